@@ -1,0 +1,134 @@
+/* fdr_b200.h -- C ABI of the B200-native frequency-domain restoration path.
+ *
+ * This is the drop-in boundary for the reference's gpu mode.  Each entry point names the
+ * reference interface it replaces (file:line under the reference repository); the C++
+ * functions of fft/fft.hpp (namespace fft_gpu) and the ./gpu CLI in this repository are thin
+ * wrappers over these calls, and INTEGRATION.md shows the binding a maintainer of the
+ * reference would add.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 (FDR_OK) or a negative FDR_E_* code; fdr_last_error() gives the
+ *     text of the calling thread's most recent failure (the C++ wrappers turn a non-zero status
+ *     into the reference's "Error: <file>:<line>, <msg>" + exit(1), fft/fft_gpu.cu:59-66);
+ *   - pointers are borrowed for the duration of the call; the plan owns all device memory;
+ *   - images are H x W, padded internally to powers of two (utils.hpp:27-31,
+ *     fft_gpu.cu:287-288); planes are fp32 in [0,1]; complex data is interleaved (re, im) fp32;
+ *   - results follow the reference's SERIAL path (fft_serial.cpp:141-261 + serial.cpp:33-39):
+ *     zero-pad, FFT, G*conj(H)/(|H|^2+K), unscaled inverse FFT, real part, min-max normalise
+ *     over the PADDED plane, crop, and for the 8-bit entry points rint(255*x) saturated;
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     FDR_E_CUDA.
+ */
+#ifndef FDR_B200_H
+#define FDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDR_OK 0
+#define FDR_E_INVALID (-1) /* bad argument */
+#define FDR_E_CUDA (-2)    /* CUDA runtime error, see fdr_last_error() */
+#define FDR_E_STATE (-3)   /* call order (e.g. restore before a PSF was set) */
+#define FDR_E_NOMEM (-4)
+
+typedef struct fdr_plan fdr_plan;
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* fdr_last_error(void);
+int fdr_version(void);
+int fdr_device_count(int* count);
+/* Pinned host memory for the host entry points (cudaMallocHost, fft_gpu.cu:304-306). */
+int fdr_host_alloc(void** ptr, size_t bytes);
+int fdr_host_free(void* ptr);
+
+/* ---- plan: sizes, workspace, Wiener factor -------------------------------------------- */
+/* rows x cols: unpadded image size; channels: planes per image (3 for BGR); max_images: upper
+ * bound of images per restore call (workspace is chunked, so this only bounds staging);
+ * device: CUDA ordinal.  Replaces the per-call cudaMalloc block of
+ * fft_gpu::wienerDeblur_RGB_optimized (fft_gpu.cu:304-322). */
+int fdr_plan_create(fdr_plan** plan, int rows, int cols, int channels, int max_images, int device);
+int fdr_plan_destroy(fdr_plan* plan);
+/* Padded sizes chosen by the plan (nextPowerOfTwo, utils.hpp:27-31). */
+int fdr_plan_padded_size(const fdr_plan* plan, int* padded_rows, int* padded_cols);
+/* Images per internal chunk (0 = automatic).  Tuning knob; results do not depend on it. */
+int fdr_plan_set_chunk_images(fdr_plan* plan, int images);
+
+/* PSF given by the caller, as motionBlurKernel() returns it (utils.hpp:15-24): psf_rows x
+ * psf_cols fp32, anchored top-left when padded (fft_serial.cpp:166-170).  Builds
+ * Wf = conj(H)/(|H|^2 + K) on the device once (the reference recomputes the PSF spectrum per
+ * channel, fft_gpu.cu:329-356). */
+int fdr_plan_set_psf_host(fdr_plan* plan, const float* psf, int psf_rows, int psf_cols, size_t psf_stride_bytes,
+                          float K);
+/* PSF built ON THE DEVICE from (length, angle) -- utils.hpp:15-24 motionBlurKernel with
+ * OpenCV's fixed-point bilinear warpAffine, bit-identical to cv2 4.13. */
+int fdr_plan_set_psf_motion(fdr_plan* plan, int length, double angle_deg, float K);
+/* Copies of plan state for inspection / parity tests. */
+int fdr_plan_get_psf_host(const fdr_plan* plan, float* psf_out, int capacity_floats, int* psf_rows, int* psf_cols);
+int fdr_plan_get_wiener_host(const fdr_plan* plan, float* wf_interleaved /* padded_rows*padded_cols*2 */);
+
+/* ---- restoration: host buffers (the reference-facing calls) --------------------------- */
+/* fft_gpu::wienerDeblur_RGB_optimized / _naive (fft/fft.hpp:32-33, fft_gpu.cu:279-394,
+ * 400-512): n_planes fp32 planes of rows x cols (row stride in bytes) in, the same number of
+ * min-max normalised fp32 planes out.  in and out may alias. */
+int fdr_restore_planes_host_f32(fdr_plan* plan, const float* const* in_planes, size_t in_stride_bytes,
+                                float* const* out_planes, size_t out_stride_bytes, int n_planes);
+/* Whole images: interleaved 8-bit [image][row][col][channel] in (as cv::imread gives,
+ * gpu.cpp:68), restored 8-bit images out (gpu.cpp:134 without the Lab stage).  The /255
+ * conversion (gpu.cpp:70-71) happens on the device. */
+int fdr_restore_images_host_u8(fdr_plan* plan, const uint8_t* in_images, uint8_t* out_images, int n_images);
+
+/* ---- restoration: device-resident buffers (benchmarks, pipelines) --------------------- */
+/* stream: a cudaStream_t (NULL = the plan's own stream).  Asynchronous with respect to the
+ * host; inputs and outputs are device pointers on the plan's device. */
+int fdr_restore_images_device_u8(fdr_plan* plan, const void* d_in_images, void* d_out_images, int n_images,
+                                 void* stream);
+/* d_in_planes: [n_planes][rows][cols] fp32 contiguous.  Either output may be NULL:
+ * d_out_planes_f32 [n_planes][rows][cols] normalised fp32; d_out_images_u8 interleaved 8-bit
+ * (n_planes must then be a multiple of the plan's channel count). */
+int fdr_restore_planes_device_f32(fdr_plan* plan, const void* d_in_planes, void* d_out_planes_f32,
+                                  void* d_out_images_u8, int n_planes, void* stream);
+/* min and max of each UN-normalised padded plane of the most recent restore chunk
+ * ([plane][2] floats, at most `capacity_planes` planes). */
+int fdr_plan_last_minmax_host(fdr_plan* plan, float* minmax, int capacity_planes);
+/* Six buckets in ms of the most recent HOST restore call, in the order of the reference's
+ * Profiler (fft_gpu.cu:17-57): alloc, H2D, pre-process, compute, D2H, post-process. */
+int fdr_plan_get_profile(const fdr_plan* plan, float ms[6]);
+/* Number of kernels the most recent restore call launched. */
+int fdr_plan_last_launch_count(const fdr_plan* plan, long long* launches);
+
+/* ---- spectra for the parity gates (1e-4 relative L2 against fft_serial) --------------- */
+/* G = FFT2(zero-padded plane) (fft_serial.cpp:176), padded_rows*padded_cols*2 floats. */
+int fdr_plan_forward_spectrum_host(fdr_plan* plan, const float* plane, size_t stride_bytes, float* G_interleaved);
+/* F = G * conj(H)/(|H|^2+K) (fft_serial.cpp:186-224). */
+int fdr_plan_filtered_spectrum_host(fdr_plan* plan, const float* plane, size_t stride_bytes, float* F_interleaved);
+
+/* ---- building blocks named after fft/fft.hpp's fft_gpu declarations ------------------- */
+/* fft_gpu::my_dft2D(Mat&, bool) (fft.hpp:40; empty stub in fft_gpu.cu:515): in-place 2-D DFT of
+ * a rows x cols interleaved complex matrix, unscaled in both directions
+ * (fft_serial.cpp:113-139). */
+int fdr_dft2d_host(float* interleaved, int rows, int cols, int inverse);
+/* fft_gpu::fft_radix2_kernel(float*, int, bool) (fft.hpp:35; stub fft_gpu.cu:514): in-place
+ * power-of-two FFT of n interleaved complex points (fft_serial.cpp:40-68). */
+int fdr_fft_radix2_host(float* interleaved, int n, int inverse);
+/* fft_gpu::dft_naive_kernel (fft.hpp:37; never defined by the reference): O(n^2) DFT of any
+ * length (fft_serial.cpp:71-87). */
+int fdr_dft_naive_host(float* interleaved, int n, int inverse);
+/* fft_gpu::transform_row_kernel (fft.hpp:39; never defined): radix-2 when n is a power of
+ * two, naive DFT otherwise (fft_serial.cpp:90-108).  `rows` independent rows. */
+int fdr_transform_rows_host(float* interleaved, int rows, int n, int inverse);
+
+/* ---- synthetic input + measurement helpers (bench, tests) ----------------------------- */
+/* Counter-hash u8 images generated on the device, identical to oracle/orc_synth_u8. */
+int fdr_synth_images_device_u8(void* d_out_images, uint32_t seed, long long first_image, int n_images, int channels,
+                               int rows, int cols, void* stream);
+/* Overwrites `bytes` of scratch to evict L2 between timed iterations. */
+int fdr_l2_flush_device(void* d_scratch, size_t bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDR_B200_H */

@@ -1,0 +1,787 @@
+// capi.cu -- plan management and the extern "C" surface declared in include/fdr_b200.h.
+//
+// Host-side orchestration only: which fused pass runs on which chunk of planes, staging for the
+// host entry points, error translation.  No arithmetic on pixel data happens on the CPU; there
+// is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/fdr_b200.h"
+#include "passes.h"
+
+using namespace fdr;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define FDR_CUDA(call)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return set_error(FDR_E_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define FDR_TRY(call)            \
+    do {                         \
+        int rc__ = (call);       \
+        if (rc__ != FDR_OK) return rc__; \
+    } while (0)
+
+int next_pow2(int n) {  // utils.hpp:27-31
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+bool g_kernels_configured[64] = {false};
+
+int ensure_device(int device) {
+    FDR_CUDA(cudaSetDevice(device));
+    if (device >= 0 && device < 64 && !g_kernels_configured[device]) {
+        FDR_CUDA(configure_pass_kernels());
+        g_kernels_configured[device] = true;
+    }
+    return FDR_OK;
+}
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return FDR_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) return set_error(FDR_E_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return FDR_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <typename T> struct PinBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count) {
+        if (count <= n) return FDR_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
+        if (e != cudaSuccess) return set_error(FDR_E_NOMEM, "cudaMallocHost(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return FDR_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+bool is_pinned_or_device(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct fdr_plan {
+    int device = 0;
+    int H = 0, W = 0, C = 0, max_images = 0;
+    int Rp = 0, Cp = 0;
+    int chunk_images_user = 0;
+    float K = 0.f;
+    int psf_rows = 0, psf_cols = 0;
+    bool have_wiener = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // device workspace
+    DevBuf<float2> spec;          // chunk pairs x Rp x Cp
+    DevBuf<float> raw;            // chunk units x H x W
+    DevBuf<unsigned int> mm;      // chunk units x 2
+    DevBuf<float2> ss;            // chunk units
+    DevBuf<float> mmf;            // chunk units x 2
+    DevBuf<float2> wiener;        // Rp x Cp
+    DevBuf<float> psf;            // psf_rows x psf_cols
+    // staging for the host entry points
+    DevBuf<uint8_t> d_in_u8, d_out_u8;
+    DevBuf<float> d_in_f32, d_out_f32;
+    PinBuf<uint8_t> h_u8_in, h_u8_out;
+    PinBuf<float> h_f32_in, h_f32_out;
+    float profile_ms[6] = {0, 0, 0, 0, 0, 0};
+    long long launches = 0;
+    int last_units = 0;
+
+    size_t plane_elems() const { return (size_t)Rp * Cp; }
+    // images per chunk: keep the complex workspace of a chunk near 96 MB (inside the 126 MB L2)
+    // but never below one image; an even unit count per chunk keeps plane pairs inside a chunk.
+    int chunk_images(int n_images_total) const {
+        int ci = chunk_images_user;
+        if (ci <= 0) {
+            const double target = 96.0 * 1024 * 1024;
+            const double per_image = 0.5 * C * (double)plane_elems() * sizeof(float2);
+            ci = (int)(target / per_image);
+            if (ci < 1) ci = 1;
+            const char* env = getenv("FDR_CHUNK_IMAGES");
+            if (env && atoi(env) > 0) ci = atoi(env);
+        }
+        if ((ci * C) % 2 && ci < n_images_total) ci += 1;
+        if (ci > n_images_total) ci = n_images_total;
+        return ci < 1 ? 1 : ci;
+    }
+};
+
+namespace {
+
+struct InputDesc {
+    int mode;  // ROW_IN_PAIR_F32 / ROW_IN_PAIR_U8
+    const float* f32 = nullptr;
+    long long unit_stride = 0, row_stride = 0;
+    const uint8_t* u8 = nullptr;
+};
+
+int ensure_workspace(fdr_plan* p, int chunk_units) {
+    const int pairs = (chunk_units + 1) / 2;
+    FDR_TRY(p->spec.ensure((size_t)pairs * p->plane_elems()));
+    FDR_TRY(p->raw.ensure((size_t)chunk_units * p->H * p->W));
+    FDR_TRY(p->mm.ensure((size_t)chunk_units * 2));
+    FDR_TRY(p->ss.ensure((size_t)chunk_units));
+    FDR_TRY(p->mmf.ensure((size_t)chunk_units * 2));
+    return FDR_OK;
+}
+
+// Restores units [0, n_units) (unit = one colour plane; image i = units i*C .. i*C+C-1).
+// out_f32: normalised planes [unit][H][W] or NULL; out_u8: interleaved images or NULL.
+int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8_t* out_u8, long long n_units,
+                         cudaStream_t s) {
+    if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set: call fdr_plan_set_psf_* first");
+    if (n_units <= 0) return FDR_OK;
+    const int C = p->C;
+    if (out_u8 && (n_units % C)) return set_error(FDR_E_INVALID, "8-bit output needs whole images (%lld planes, %d channels)", n_units, C);
+    const long long n_images = (n_units + C - 1) / C;
+    long long chunk_units = (long long)p->chunk_images((int)n_images) * C;
+    if (chunk_units > n_units) chunk_units = n_units;
+    if (!out_u8 && (chunk_units % 2) && chunk_units < n_units) chunk_units += 1;
+    FDR_TRY(ensure_workspace(p, (int)chunk_units));
+    p->launches = 0;
+    const long long HW = (long long)p->H * p->W;
+    for (long long base = 0; base < n_units; base += chunk_units) {
+        const int nu = (int)((n_units - base < chunk_units) ? (n_units - base) : chunk_units);
+        const int np = (nu + 1) / 2;
+        FDR_CUDA(launch_minmax_reset(p->mm.p, nu, s));
+        RowPassArgs r1{};
+        r1.n = p->Cp;
+        r1.nrows = p->H;
+        r1.npairs = np;
+        r1.in_mode = in.mode;
+        r1.out_mode = ROW_OUT_COMPLEX;
+        r1.in_f32 = in.f32;
+        r1.in_unit_stride = in.unit_stride;
+        r1.in_row_stride = in.row_stride;
+        r1.in_u8 = in.u8;
+        r1.channels = C;
+        r1.img_rows = p->H;
+        r1.img_cols = p->W;
+        r1.unit_base = base;
+        r1.units_total = n_units;
+        r1.cout = p->spec.p;
+        r1.cplane = (long long)p->plane_elems();
+        FDR_CUDA(launch_row_pass(r1, s));
+
+        ColPassArgs c2{};
+        c2.n = p->Rp;
+        c2.pitch = p->Cp;
+        c2.npairs = np;
+        c2.mode = COL_WIENER;
+        c2.rows_valid = p->H;
+        c2.data = p->spec.p;
+        c2.cplane = (long long)p->plane_elems();
+        c2.wiener = p->wiener.p;
+        c2.K = p->K;
+        FDR_CUDA(launch_col_pass(c2, s));
+
+        RowPassArgs r3{};
+        r3.n = p->Cp;
+        r3.nrows = p->Rp;
+        r3.npairs = np;
+        r3.in_mode = ROW_IN_COMPLEX;
+        r3.out_mode = ROW_OUT_REAL_PAIR;
+        r3.cin = p->spec.p;
+        r3.cplane = (long long)p->plane_elems();
+        r3.unit_base = base;
+        r3.units_total = n_units;
+        r3.raw = p->raw.p;
+        r3.raw_unit_stride = HW;
+        r3.raw_rows = p->H;
+        r3.raw_cols = p->W;
+        r3.minmax = p->mm.p;
+        r3.local_units = nu;
+        FDR_CUDA(launch_row_pass(r3, s));
+
+        FDR_CUDA(launch_minmax_finalize(p->mm.p, p->ss.p, p->mmf.p, nu, s));
+        p->launches += 5;
+        if (out_u8) {
+            FDR_CUDA(launch_pack_u8(p->raw.p, HW, p->ss.p, out_u8 + base * HW, nu / C, C, p->H, p->W, s));
+            p->launches += 1;
+        }
+        if (out_f32) {
+            FDR_CUDA(launch_normalize_f32(p->raw.p, HW, p->ss.p, out_f32 + base * HW, HW, nu, p->H, p->W, s));
+            p->launches += 1;
+        }
+        p->last_units = nu;
+    }
+    return FDR_OK;
+}
+
+int build_wiener(fdr_plan* p) {
+    if (p->psf_rows > p->Rp || p->psf_cols > p->Cp)
+        return set_error(FDR_E_INVALID, "PSF %dx%d larger than the padded image %dx%d", p->psf_rows, p->psf_cols, p->Rp, p->Cp);
+    FDR_TRY(p->wiener.ensure(p->plane_elems()));
+    FDR_TRY(p->spec.ensure(p->plane_elems()));
+    cudaStream_t s = p->stream;
+    RowPassArgs r{};
+    r.n = p->Cp;
+    r.nrows = p->psf_rows;
+    r.npairs = 1;
+    r.in_mode = ROW_IN_PAIR_F32;
+    r.out_mode = ROW_OUT_COMPLEX;
+    r.in_f32 = p->psf.p;
+    r.in_unit_stride = (long long)p->psf_rows * p->psf_cols;
+    r.in_row_stride = p->psf_cols;
+    r.channels = 1;
+    r.img_rows = p->psf_rows;
+    r.img_cols = p->psf_cols;
+    r.unit_base = 0;
+    r.units_total = 1;
+    r.cout = p->spec.p;
+    r.cplane = (long long)p->plane_elems();
+    FDR_CUDA(launch_row_pass(r, s));
+    ColPassArgs c{};
+    c.n = p->Rp;
+    c.pitch = p->Cp;
+    c.npairs = 1;
+    c.mode = COL_MAKE_WIENER;
+    c.rows_valid = p->psf_rows;
+    c.data = p->spec.p;
+    c.cplane = (long long)p->plane_elems();
+    c.wiener_out = p->wiener.p;
+    c.K = p->K;
+    FDR_CUDA(launch_col_pass(c, s));
+    FDR_CUDA(cudaStreamSynchronize(s));
+    p->have_wiener = true;
+    return FDR_OK;
+}
+
+// Inverse rotation matrix exactly as OpenCV derives it (getRotationMatrix2D + warpAffine's
+// inversion, both in double); utils.hpp:16-22.
+PsfAffine motion_affine(int size, double angle_deg) {
+    const double CVPI = 3.1415926535897932384626433832795;
+    const double cx = (double)(float)(size / 2), cy = (double)(float)(size / 2);
+    double ang = angle_deg * (CVPI / 180);
+    double alpha = std::cos(ang), beta = std::sin(ang);
+    double M[6] = {alpha, beta, (1 - alpha) * cx - beta * cy, -beta, alpha, beta * cx + (1 - alpha) * cy};
+    double D = M[0] * M[4] - M[1] * M[3];
+    D = D != 0 ? 1. / D : 0;
+    double A11 = M[4] * D, A22 = M[0] * D;
+    M[0] = A11;
+    M[1] *= -D;
+    M[3] *= -D;
+    M[4] = A22;
+    double b1 = -M[0] * M[2] - M[1] * M[5];
+    double b2 = -M[3] * M[2] - M[4] * M[5];
+    PsfAffine a;
+    a.a00 = M[0];
+    a.a01 = M[1];
+    a.b0 = b1;
+    a.a10 = M[3];
+    a.a11 = M[4];
+    a.b1 = b2;
+    return a;
+}
+
+struct ScopedTimer {  // event pair on a stream, accumulating into a bucket (Profiler, fft_gpu.cu:17-57)
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    float* dst;
+    ScopedTimer(fdr_plan* p, int slot, cudaStream_t st, float* d) : a(p->ev[2 * slot]), b(p->ev[2 * slot + 1]), s(st), dst(d) {
+        cudaEventRecord(a, s);
+    }
+    void stop() {
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        *dst += ms;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+__attribute__((visibility("default"))) const char* fdr_last_error(void) { return g_last_error.c_str(); }
+__attribute__((visibility("default"))) int fdr_version(void) { return 100; }
+
+__attribute__((visibility("default"))) int fdr_device_count(int* count) {
+    if (!count) return set_error(FDR_E_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return set_error(FDR_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return set_error(FDR_E_INVALID, "ptr is NULL");
+    FDR_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return FDR_OK;
+}
+__attribute__((visibility("default"))) int fdr_host_free(void* ptr) {
+    if (ptr) FDR_CUDA(cudaFreeHost(ptr));
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int rows, int cols, int channels, int max_images, int device) {
+    if (!plan) return set_error(FDR_E_INVALID, "plan is NULL");
+    *plan = nullptr;
+    if (rows < 1 || cols < 1 || channels < 1 || max_images < 1)
+        return set_error(FDR_E_INVALID, "rows=%d cols=%d channels=%d max_images=%d must all be >= 1", rows, cols, channels, max_images);
+    if (rows > 16384 || cols > 16384) return set_error(FDR_E_INVALID, "padded size above 16384 is not supported (%dx%d)", rows, cols);
+    FDR_TRY(ensure_device(device));
+    fdr_plan* p = new (std::nothrow) fdr_plan();
+    if (!p) return set_error(FDR_E_NOMEM, "out of host memory");
+    p->device = device;
+    p->H = rows;
+    p->W = cols;
+    p->C = channels;
+    p->max_images = max_images;
+    p->Rp = next_pow2(rows);
+    p->Cp = next_pow2(cols);
+    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&p->ev[i]);
+    if (e != cudaSuccess) {
+        delete p;
+        return set_error(FDR_E_CUDA, "plan stream/event creation: %s", cudaGetErrorString(e));
+    }
+    *plan = p;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
+    if (!p) return FDR_OK;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    p->spec.release();
+    p->raw.release();
+    p->mm.release();
+    p->ss.release();
+    p->mmf.release();
+    p->wiener.release();
+    p->psf.release();
+    p->d_in_u8.release();
+    p->d_out_u8.release();
+    p->d_in_f32.release();
+    p->d_out_f32.release();
+    p->h_u8_in.release();
+    p->h_u8_out.release();
+    p->h_f32_in.release();
+    p->h_f32_out.release();
+    for (int i = 0; i < 8; ++i)
+        if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_padded_size(const fdr_plan* p, int* pr, int* pc) {
+    if (!p) return set_error(FDR_E_INVALID, "plan is NULL");
+    if (pr) *pr = p->Rp;
+    if (pc) *pc = p->Cp;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_set_chunk_images(fdr_plan* p, int images) {
+    if (!p || images < 0) return set_error(FDR_E_INVALID, "bad plan or chunk size");
+    p->chunk_images_user = images;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_set_psf_host(fdr_plan* p, const float* psf, int psf_rows, int psf_cols, size_t stride_bytes, float K) {
+    if (!p || !psf || psf_rows < 1 || psf_cols < 1) return set_error(FDR_E_INVALID, "bad PSF arguments");
+    if (stride_bytes == 0) stride_bytes = (size_t)psf_cols * sizeof(float);
+    FDR_TRY(ensure_device(p->device));
+    FDR_TRY(p->psf.ensure((size_t)psf_rows * psf_cols));
+    FDR_CUDA(cudaMemcpy2DAsync(p->psf.p, (size_t)psf_cols * sizeof(float), psf, stride_bytes, (size_t)psf_cols * sizeof(float),
+                               psf_rows, cudaMemcpyHostToDevice, p->stream));
+    FDR_CUDA(cudaStreamSynchronize(p->stream));
+    p->psf_rows = psf_rows;
+    p->psf_cols = psf_cols;
+    p->K = K;
+    p->have_wiener = false;
+    return build_wiener(p);
+}
+
+__attribute__((visibility("default"))) int fdr_plan_set_psf_motion(fdr_plan* p, int length, double angle_deg, float K) {
+    if (!p || length < 1) return set_error(FDR_E_INVALID, "bad PSF length %d", length);
+    FDR_TRY(ensure_device(p->device));
+    FDR_TRY(p->psf.ensure((size_t)length * length));
+    FDR_CUDA(launch_motion_psf(p->psf.p, length, motion_affine(length, angle_deg), p->stream));
+    p->psf_rows = p->psf_cols = length;
+    p->K = K;
+    p->have_wiener = false;
+    return build_wiener(p);
+}
+
+__attribute__((visibility("default"))) int fdr_plan_get_psf_host(const fdr_plan* p, float* out, int capacity, int* rows, int* cols) {
+    if (!p) return set_error(FDR_E_INVALID, "plan is NULL");
+    if (p->psf_rows == 0) return set_error(FDR_E_STATE, "no PSF set");
+    if (rows) *rows = p->psf_rows;
+    if (cols) *cols = p->psf_cols;
+    if (out) {
+        if (capacity < p->psf_rows * p->psf_cols) return set_error(FDR_E_INVALID, "PSF buffer too small");
+        FDR_CUDA(cudaSetDevice(p->device));
+        FDR_CUDA(cudaMemcpy(out, p->psf.p, sizeof(float) * (size_t)p->psf_rows * p->psf_cols, cudaMemcpyDeviceToHost));
+    }
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_get_wiener_host(const fdr_plan* p, float* wf) {
+    if (!p || !wf) return set_error(FDR_E_INVALID, "bad arguments");
+    if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
+    FDR_CUDA(cudaSetDevice(p->device));
+    FDR_CUDA(cudaMemcpy(wf, p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_restore_images_device_u8(fdr_plan* p, const void* d_in, void* d_out, int n_images, void* stream) {
+    if (!p || !d_in || !d_out || n_images < 0) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_TRY(ensure_device(p->device));
+    InputDesc in;
+    in.mode = ROW_IN_PAIR_U8;
+    in.u8 = static_cast<const uint8_t*>(d_in);
+    return restore_units_device(p, in, nullptr, static_cast<uint8_t*>(d_out), (long long)n_images * p->C,
+                                stream ? static_cast<cudaStream_t>(stream) : p->stream);
+}
+
+__attribute__((visibility("default"))) int fdr_restore_planes_device_f32(fdr_plan* p, const void* d_in, void* d_out_f32, void* d_out_u8, int n_planes, void* stream) {
+    if (!p || !d_in || n_planes < 0 || (!d_out_f32 && !d_out_u8)) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_TRY(ensure_device(p->device));
+    InputDesc in;
+    in.mode = ROW_IN_PAIR_F32;
+    in.f32 = static_cast<const float*>(d_in);
+    in.unit_stride = (long long)p->H * p->W;
+    in.row_stride = p->W;
+    return restore_units_device(p, in, static_cast<float*>(d_out_f32), static_cast<uint8_t*>(d_out_u8), n_planes,
+                                stream ? static_cast<cudaStream_t>(stream) : p->stream);
+}
+
+__attribute__((visibility("default"))) int fdr_restore_planes_host_f32(fdr_plan* p, const float* const* in_planes, size_t in_stride, float* const* out_planes,
+                                size_t out_stride, int n_planes) {
+    if (!p || !in_planes || !out_planes || n_planes < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_TRY(ensure_device(p->device));
+    const size_t HW = (size_t)p->H * p->W, rowb = (size_t)p->W * sizeof(float);
+    if (in_stride == 0) in_stride = rowb;
+    if (out_stride == 0) out_stride = rowb;
+    if (in_stride < rowb || out_stride < rowb) return set_error(FDR_E_INVALID, "row stride smaller than a row");
+    cudaStream_t s = p->stream;
+    for (int i = 0; i < 6; ++i) p->profile_ms[i] = 0.f;
+    {
+        ScopedTimer t(p, 0, s, &p->profile_ms[0]);
+        FDR_TRY(p->d_in_f32.ensure(HW * n_planes));
+        FDR_TRY(p->d_out_f32.ensure(HW * n_planes));
+        FDR_TRY(p->h_f32_in.ensure(HW * n_planes));
+        FDR_TRY(p->h_f32_out.ensure(HW * n_planes));
+        t.stop();
+    }
+    {
+        ScopedTimer t(p, 1, s, &p->profile_ms[1]);
+        for (int u = 0; u < n_planes; ++u) {
+            if (!in_planes[u] || !out_planes[u]) return set_error(FDR_E_INVALID, "plane %d is NULL", u);
+            for (int y = 0; y < p->H; ++y)
+                memcpy(p->h_f32_in.p + u * HW + (size_t)y * p->W, reinterpret_cast<const char*>(in_planes[u]) + y * in_stride, rowb);
+        }
+        FDR_CUDA(cudaMemcpyAsync(p->d_in_f32.p, p->h_f32_in.p, HW * n_planes * sizeof(float), cudaMemcpyHostToDevice, s));
+        t.stop();
+    }
+    {
+        ScopedTimer t(p, 2, s, &p->profile_ms[3]);
+        InputDesc in;
+        in.mode = ROW_IN_PAIR_F32;
+        in.f32 = p->d_in_f32.p;
+        in.unit_stride = (long long)HW;
+        in.row_stride = p->W;
+        FDR_TRY(restore_units_device(p, in, p->d_out_f32.p, nullptr, n_planes, s));
+        t.stop();
+    }
+    {
+        ScopedTimer t(p, 3, s, &p->profile_ms[4]);
+        FDR_CUDA(cudaMemcpyAsync(p->h_f32_out.p, p->d_out_f32.p, HW * n_planes * sizeof(float), cudaMemcpyDeviceToHost, s));
+        t.stop();
+    }
+    {
+        ScopedTimer t(p, 0, s, &p->profile_ms[5]);
+        for (int u = 0; u < n_planes; ++u)
+            for (int y = 0; y < p->H; ++y)
+                memcpy(reinterpret_cast<char*>(out_planes[u]) + y * out_stride, p->h_f32_out.p + u * HW + (size_t)y * p->W, rowb);
+        t.stop();
+    }
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_restore_images_host_u8(fdr_plan* p, const uint8_t* in_images, uint8_t* out_images, int n_images) {
+    if (!p || !in_images || !out_images || n_images < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_TRY(ensure_device(p->device));
+    const size_t bytes = (size_t)p->H * p->W * p->C * n_images;
+    cudaStream_t s = p->stream;
+    for (int i = 0; i < 6; ++i) p->profile_ms[i] = 0.f;
+    FDR_TRY(p->d_in_u8.ensure(bytes));
+    FDR_TRY(p->d_out_u8.ensure(bytes));
+    const uint8_t* src = in_images;
+    uint8_t* dst = out_images;
+    const bool in_direct = is_pinned_or_device(in_images), out_direct = is_pinned_or_device(out_images);
+    if (!in_direct) {
+        FDR_TRY(p->h_u8_in.ensure(bytes));
+        memcpy(p->h_u8_in.p, in_images, bytes);
+        src = p->h_u8_in.p;
+    }
+    if (!out_direct) {
+        FDR_TRY(p->h_u8_out.ensure(bytes));
+        dst = p->h_u8_out.p;
+    }
+    {
+        ScopedTimer t(p, 1, s, &p->profile_ms[1]);
+        FDR_CUDA(cudaMemcpyAsync(p->d_in_u8.p, src, bytes, cudaMemcpyHostToDevice, s));
+        t.stop();
+    }
+    {
+        ScopedTimer t(p, 2, s, &p->profile_ms[3]);
+        InputDesc in;
+        in.mode = ROW_IN_PAIR_U8;
+        in.u8 = p->d_in_u8.p;
+        FDR_TRY(restore_units_device(p, in, nullptr, p->d_out_u8.p, (long long)n_images * p->C, s));
+        t.stop();
+    }
+    {
+        ScopedTimer t(p, 3, s, &p->profile_ms[4]);
+        FDR_CUDA(cudaMemcpyAsync(dst, p->d_out_u8.p, bytes, cudaMemcpyDeviceToHost, s));
+        t.stop();
+    }
+    if (!out_direct) memcpy(out_images, p->h_u8_out.p, bytes);
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_last_minmax_host(fdr_plan* p, float* minmax, int capacity_planes) {
+    if (!p || !minmax) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_CUDA(cudaSetDevice(p->device));
+    FDR_CUDA(cudaStreamSynchronize(p->stream));
+    int n = p->last_units < capacity_planes ? p->last_units : capacity_planes;
+    if (n > 0) FDR_CUDA(cudaMemcpy(minmax, p->mmf.p, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_get_profile(const fdr_plan* p, float ms[6]) {
+    if (!p || !ms) return set_error(FDR_E_INVALID, "bad arguments");
+    for (int i = 0; i < 6; ++i) ms[i] = p->profile_ms[i];
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_last_launch_count(const fdr_plan* p, long long* launches) {
+    if (!p || !launches) return set_error(FDR_E_INVALID, "bad arguments");
+    *launches = p->launches;
+    return FDR_OK;
+}
+
+static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* out, int col_mode) {
+    if (!p || !plane || !out) return set_error(FDR_E_INVALID, "bad arguments");
+    if (col_mode == COL_FILTER && !p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
+    FDR_TRY(ensure_device(p->device));
+    const size_t HW = (size_t)p->H * p->W, rowb = (size_t)p->W * sizeof(float);
+    if (stride == 0) stride = rowb;
+    cudaStream_t s = p->stream;
+    FDR_TRY(p->d_in_f32.ensure(HW));
+    FDR_TRY(p->spec.ensure(p->plane_elems()));
+    FDR_CUDA(cudaMemcpy2DAsync(p->d_in_f32.p, rowb, plane, stride, rowb, p->H, cudaMemcpyHostToDevice, s));
+    RowPassArgs r{};
+    r.n = p->Cp;
+    r.nrows = p->H;
+    r.npairs = 1;
+    r.in_mode = ROW_IN_PAIR_F32;
+    r.out_mode = ROW_OUT_COMPLEX;
+    r.in_f32 = p->d_in_f32.p;
+    r.in_unit_stride = (long long)HW;
+    r.in_row_stride = p->W;
+    r.channels = 1;
+    r.img_rows = p->H;
+    r.img_cols = p->W;
+    r.units_total = 1;
+    r.cout = p->spec.p;
+    r.cplane = (long long)p->plane_elems();
+    FDR_CUDA(launch_row_pass(r, s));
+    ColPassArgs c{};
+    c.n = p->Rp;
+    c.pitch = p->Cp;
+    c.npairs = 1;
+    c.mode = col_mode;
+    c.rows_valid = p->H;
+    c.data = p->spec.p;
+    c.cplane = (long long)p->plane_elems();
+    c.wiener = p->wiener.p;
+    FDR_CUDA(launch_col_pass(c, s));
+    FDR_CUDA(cudaMemcpyAsync(out, p->spec.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost, s));
+    FDR_CUDA(cudaStreamSynchronize(s));
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_forward_spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* G) {
+    return spectrum_host(p, plane, stride, G, COL_FFT);
+}
+__attribute__((visibility("default"))) int fdr_plan_filtered_spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* F) {
+    return spectrum_host(p, plane, stride, F, COL_FILTER);
+}
+
+// ---- building blocks ----------------------------------------------------------------------
+
+// rows x n complex, transform every row (in place on the device buffer d).
+static int rows_device(float2* d, float2* tmp, int rows, int n, int inverse, cudaStream_t s) {
+    if (is_pow2(n)) {
+        RowPassArgs r{};
+        r.n = n;
+        r.nrows = rows;
+        r.npairs = 1;
+        r.in_mode = ROW_IN_COMPLEX;
+        r.out_mode = ROW_OUT_COMPLEX;
+        r.conj_in = r.conj_out = inverse ? 1 : 0;
+        r.cin = d;
+        r.cout = d;
+        r.cplane = (long long)rows * n;
+        FDR_CUDA(launch_row_pass(r, s));
+    } else {
+        FDR_CUDA(launch_dft_naive(d, tmp, n, 1, rows, n, inverse, s));
+        FDR_CUDA(cudaMemcpyAsync(d, tmp, sizeof(float2) * (size_t)rows * n, cudaMemcpyDeviceToDevice, s));
+    }
+    return FDR_OK;
+}
+
+static int cols_device(float2* d, float2* tmp, int rows, int cols, int inverse, cudaStream_t s) {
+    if (is_pow2(rows)) {
+        ColPassArgs c{};
+        c.n = rows;
+        c.pitch = cols;
+        c.npairs = 1;
+        c.mode = COL_FFT;
+        c.conj_in = c.conj_out = inverse ? 1 : 0;
+        c.rows_valid = rows;
+        c.data = d;
+        c.cplane = (long long)rows * cols;
+        FDR_CUDA(launch_col_pass(c, s));
+    } else {
+        FDR_CUDA(launch_dft_naive(d, tmp, rows, cols, cols, 1, inverse, s));
+        FDR_CUDA(cudaMemcpyAsync(d, tmp, sizeof(float2) * (size_t)rows * cols, cudaMemcpyDeviceToDevice, s));
+    }
+    return FDR_OK;
+}
+
+static int transform_host(float* data, int rows, int cols, int inverse, bool do_rows, bool do_cols) {
+    if (!data || rows < 1 || cols < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    if ((is_pow2(cols) && cols > 16384) || (is_pow2(rows) && do_cols && rows > 16384))
+        return set_error(FDR_E_INVALID, "power-of-two lengths above 16384 are not supported");
+    int dev = 0;
+    FDR_CUDA(cudaGetDevice(&dev));
+    FDR_TRY(ensure_device(dev));
+    const size_t n = (size_t)rows * cols;
+    float2 *d = nullptr, *tmp = nullptr;
+    FDR_CUDA(cudaMalloc(&d, n * sizeof(float2)));
+    const bool need_tmp = (do_rows && !is_pow2(cols)) || (do_cols && !is_pow2(rows));
+    int rc = FDR_OK;
+    cudaError_t e = cudaSuccess;
+    if (need_tmp) e = cudaMalloc(&tmp, n * sizeof(float2));
+    if (e != cudaSuccess) rc = set_error(FDR_E_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e));
+    if (rc == FDR_OK) {
+        e = cudaMemcpy(d, data, n * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "H2D: %s", cudaGetErrorString(e));
+    }
+    if (rc == FDR_OK && do_rows) rc = rows_device(d, tmp, rows, cols, inverse, 0);
+    if (rc == FDR_OK && do_cols) rc = cols_device(d, tmp, rows, cols, inverse, 0);
+    if (rc == FDR_OK) {
+        e = cudaMemcpy(data, d, n * sizeof(float2), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "D2H: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    if (tmp) cudaFree(tmp);
+    return rc;
+}
+
+__attribute__((visibility("default"))) int fdr_dft2d_host(float* data, int rows, int cols, int inverse) { return transform_host(data, rows, cols, inverse, true, true); }
+
+__attribute__((visibility("default"))) int fdr_fft_radix2_host(float* data, int n, int inverse) {
+    if (!is_pow2(n)) return set_error(FDR_E_INVALID, "fft_radix2 needs a power-of-two length, got %d", n);
+    return transform_host(data, 1, n, inverse, true, false);
+}
+
+__attribute__((visibility("default"))) int fdr_dft_naive_host(float* data, int n, int inverse) {
+    if (!data || n < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    int dev = 0;
+    FDR_CUDA(cudaGetDevice(&dev));
+    FDR_TRY(ensure_device(dev));
+    float2 *d = nullptr, *o = nullptr;
+    FDR_CUDA(cudaMalloc(&d, sizeof(float2) * n));
+    FDR_CUDA(cudaMalloc(&o, sizeof(float2) * n));
+    FDR_CUDA(cudaMemcpy(d, data, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    FDR_CUDA(launch_dft_naive(d, o, n, 1, 1, n, inverse, 0));
+    FDR_CUDA(cudaMemcpy(data, o, sizeof(float2) * n, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    cudaFree(o);
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_transform_rows_host(float* data, int rows, int n, int inverse) { return transform_host(data, rows, n, inverse, true, false); }
+
+__attribute__((visibility("default"))) int fdr_synth_images_device_u8(void* d_out, uint32_t seed, long long first_image, int n_images, int channels, int rows,
+                               int cols, void* stream) {
+    if (!d_out || n_images < 0 || channels < 1 || rows < 1 || cols < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    if (n_images == 0) return FDR_OK;
+    FDR_CUDA(launch_synth_u8(static_cast<uint8_t*>(d_out), seed, first_image, n_images, channels, rows, cols,
+                             static_cast<cudaStream_t>(stream)));
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_l2_flush_device(void* d_scratch, size_t bytes, void* stream) {
+    if (!d_scratch || bytes < 16) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_CUDA(launch_l2_flush(d_scratch, bytes, static_cast<cudaStream_t>(stream)));
+    return FDR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// kernels_misc.cu -- PSF build, min/max bookkeeping, normalise + pack, synthetic input,
+// naive DFT for non power-of-two lengths, L2 flush.
+#include <float.h>
+
+#include "passes.h"
+
+namespace fdr {
+
+// ---------------------------------------------------------------------------------
+// Motion-blur PSF (reference utils.hpp:15-24: S x S zeros, row S/2 = 1/S, rotated about
+// (S/2,S/2) with getRotationMatrix2D + warpAffine defaults).  OpenCV evaluates the warp in
+// fixed point (AB_BITS = 10, INTER_BITS = 5); this kernel reproduces that arithmetic so the
+// result is bit-identical to cv2 4.13 (tests/golden/psf_*.npy).  The inverse matrix comes
+// from the host in double; products and sums below are individually rounded (no FMA).
+// ---------------------------------------------------------------------------------
+__global__ void motion_psf_kernel(float* psf, int S, PsfAffine M) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= S || y >= S) return;
+    const double AB = 1024.0;
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M.a01, (double)y), M.b0), AB)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(M.a11, (double)y), M.b1), AB)) + 16;
+    const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(M.a00, (double)x), AB));
+    const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(M.a10, (double)x), AB));
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = X >> 5, sy = Y >> 5;
+    const float fx = (float)(X & 31) * (1.f / 32.f), fy = (float)(Y & 31) * (1.f / 32.f);
+    const float w00 = __fmul_rn(1.f - fy, 1.f - fx), w01 = __fmul_rn(1.f - fy, fx);
+    const float w10 = __fmul_rn(fy, 1.f - fx), w11 = __fmul_rn(fy, fx);
+    // source kernel: only row S/2 is non-zero, value (float)(1.0/S)
+    const float val = (float)(1.0 / (double)S);
+    const int cy = S / 2;
+    const bool xin0 = (sx >= 0 && sx < S), xin1 = (sx + 1 >= 0 && sx + 1 < S);
+    const float t00 = (sy == cy && xin0) ? val : 0.f;
+    const float t01 = (sy == cy && xin1) ? val : 0.f;
+    const float t10 = (sy + 1 == cy && xin0) ? val : 0.f;
+    const float t11 = (sy + 1 == cy && xin1) ? val : 0.f;
+    float acc = __fmul_rn(t00, w00);
+    acc = __fadd_rn(acc, __fmul_rn(t01, w01));
+    acc = __fadd_rn(acc, __fmul_rn(t10, w10));
+    acc = __fadd_rn(acc, __fmul_rn(t11, w11));
+    psf[(size_t)y * S + x] = acc;
+}
+
+cudaError_t launch_motion_psf(float* psf, int size, PsfAffine m, cudaStream_t s) {
+    dim3 b(16, 16), g((size + 15) / 16, (size + 15) / 16);
+    motion_psf_kernel<<<g, b, 0, s>>>(psf, size, m);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// min/max bookkeeping.  Pass 3 keeps per-plane extrema as order-preserving uints.
+// ---------------------------------------------------------------------------------
+__global__ void minmax_reset_kernel(unsigned int* mm, int units) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < units) {
+        mm[2 * i] = 0xFFFFFFFFu;
+        mm[2 * i + 1] = 0u;
+    }
+}
+cudaError_t launch_minmax_reset(unsigned int* minmax, int units, cudaStream_t s) {
+    minmax_reset_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax, units);
+    return cudaGetLastError();
+}
+
+__device__ __forceinline__ float f32_from_ordered(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// cv::normalize(NORM_MINMAX, 0, 1) (fft_serial.cpp:246): scale = 1/(max-min) in double
+// (0 when the range <= DBL_EPSILON), shift = -min*scale, both then rounded to float.
+__global__ void minmax_finalize_kernel(const unsigned int* mm, float2* ss, float* mmf, int units) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= units) return;
+    const double smin = (double)f32_from_ordered(mm[2 * i]);
+    const double smax = (double)f32_from_ordered(mm[2 * i + 1]);
+    const double scale = (smax - smin) > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0;
+    const double shift = 0.0 - smin * scale;
+    ss[i] = make_float2((float)scale, (float)shift);
+    if (mmf) {
+        mmf[2 * i] = (float)smin;
+        mmf[2 * i + 1] = (float)smax;
+    }
+}
+cudaError_t launch_minmax_finalize(const unsigned int* minmax, float2* scale_shift, float* minmax_f32, int units,
+                                   cudaStream_t s) {
+    minmax_finalize_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax, scale_shift, minmax_f32, units);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// Pass 4a: normalise (one fused multiply-add, as cv2's convertTo) + 8-bit pack
+// u8 = saturate(rint(255 * n))  (serial.cpp:54 convertTo(CV_8U, 255.0)).
+// Output interleaved [img][H][W][C], B,G,R order = unit order.
+// ---------------------------------------------------------------------------------
+template <int C>
+__global__ void pack_u8_kernel(const float* raw, long long ustride, const float2* ss, uint8_t* out, int rows, int cols) {
+    const int img = blockIdx.y;
+    const long long npx = (long long)rows * cols;
+    const float* r = raw + (long long)img * C * ustride;
+    uint8_t* o = out + (long long)img * npx * C;
+    float2 k[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) k[c] = ss[img * C + c];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float n = fmaf(__ldg(r + c * ustride + i), k[c].x, k[c].y);
+            int q = __float2int_rn(n * 255.0f);
+            q = min(max(q, 0), 255);
+            o[i * C + c] = (uint8_t)q;
+        }
+    }
+}
+
+__global__ void pack_u8_generic_kernel(const float* raw, long long ustride, const float2* ss, uint8_t* out, int C,
+                                       int rows, int cols) {
+    const int img = blockIdx.y;
+    const long long npx = (long long)rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x)
+        for (int c = 0; c < C; ++c) {
+            const float2 k = ss[img * C + c];
+            const float n = fmaf(raw[((long long)img * C + c) * ustride + i], k.x, k.y);
+            int q = __float2int_rn(n * 255.0f);
+            out[((long long)img * npx + i) * C + c] = (uint8_t)min(max(q, 0), 255);
+        }
+}
+
+cudaError_t launch_pack_u8(const float* raw, long long raw_unit_stride, const float2* scale_shift, uint8_t* out,
+                           int imgs, int channels, int rows, int cols, cudaStream_t s) {
+    const long long npx = (long long)rows * cols;
+    int bx = (int)((npx + 255) / 256);
+    if (bx > 148 * 8) bx = 148 * 8;
+    dim3 g(bx, imgs);
+    if (channels == 3)
+        pack_u8_kernel<3><<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, out, rows, cols);
+    else if (channels == 1)
+        pack_u8_kernel<1><<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, out, rows, cols);
+    else
+        pack_u8_generic_kernel<<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, out, channels, rows, cols);
+    return cudaGetLastError();
+}
+
+// Pass 4b: normalised f32 planes (what fft_gpu::wienerDeblur_RGB_* hands back, fft_gpu.cu:379-384).
+__global__ void normalize_f32_kernel(const float* raw, long long ustride, const float2* ss, float* out,
+                                     long long ostride, long long npx) {
+    const int u = blockIdx.y;
+    const float2 k = ss[u];
+    const float* r = raw + (long long)u * ustride;
+    float* o = out + (long long)u * ostride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x)
+        o[i] = fmaf(__ldg(r + i), k.x, k.y);
+}
+cudaError_t launch_normalize_f32(const float* raw, long long raw_unit_stride, const float2* scale_shift, float* out,
+                                 long long out_unit_stride, int units, int rows, int cols, cudaStream_t s) {
+    const long long npx = (long long)rows * cols;
+    int bx = (int)((npx + 255) / 256);
+    if (bx > 148 * 8) bx = 148 * 8;
+    dim3 g(bx, units);
+    normalize_f32_kernel<<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, out, out_unit_stride, npx);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// Synthetic input: counter hash, iid uniform u8, reproducible on the host
+// (oracle/wiener_oracle.c orc_synth_u8).  idx = ((img*C + c)*H + y)*W + x.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lowbias32(uint32_t v) {
+    v ^= v >> 16;
+    v *= 0x7feb352dU;
+    v ^= v >> 15;
+    v *= 0x846ca68bU;
+    v ^= v >> 16;
+    return v;
+}
+__global__ void synth_u8_kernel(uint8_t* out, uint32_t seed, long long img0, int C, long long npx) {
+    const int img = blockIdx.y;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x)
+        for (int c = 0; c < C; ++c) {
+            const unsigned long long idx = ((unsigned long long)(img0 + img) * C + c) * (unsigned long long)npx + i;
+            const uint32_t hi = lowbias32(seed + (uint32_t)(idx >> 32));
+            out[((long long)img * npx + i) * C + c] = (uint8_t)(lowbias32((uint32_t)idx ^ hi) >> 24);
+        }
+}
+cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, int rows, int cols,
+                            cudaStream_t s) {
+    const long long npx = (long long)rows * cols;
+    int bx = (int)((npx + 255) / 256);
+    if (bx > 148 * 8) bx = 148 * 8;
+    dim3 g(bx, imgs);
+    synth_u8_kernel<<<g, 256, 0, s>>>(out, seed, img0, channels, npx);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------
+// O(n^2) DFT for lengths that are not powers of two (fft_serial.cpp:71-87 / the declared
+// but undefined fft_gpu::dft_naive_kernel, fft.hpp:36).  Not on the hot path.
+// ---------------------------------------------------------------------------------
+__global__ void dft_naive_kernel(const float2* in, float2* out, int n, long long elem_stride, long long batch_stride,
+                                 int inverse) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float2* src = in + (long long)blockIdx.y * batch_stride;
+    float2* dst = out + (long long)blockIdx.y * batch_stride;
+    float sr = 0.f, si = 0.f;
+    for (int t = 0; t < n; ++t) {
+        const long long kt = ((long long)k * t) % n;  // exact angle reduction
+        float s, c;
+        sincospif(2.0f * (float)kt / (float)n, &s, &c);
+        if (!inverse) s = -s;
+        const float2 a = src[(long long)t * elem_stride];
+        sr += a.x * c - a.y * s;
+        si += a.x * s + a.y * c;
+    }
+    dst[(long long)k * elem_stride] = make_float2(sr, si);
+}
+cudaError_t launch_dft_naive(const float2* in, float2* out, int n, long long elem_stride, int batch,
+                             long long batch_stride, int inverse, cudaStream_t s) {
+    dim3 g((n + 127) / 128, batch);
+    dft_naive_kernel<<<g, 128, 0, s>>>(in, out, n, elem_stride, batch_stride, inverse);
+    return cudaGetLastError();
+}
+
+__global__ void l2_flush_kernel(uint4* p, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4((unsigned)i, 0u, 0u, 0u);
+}
+cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t s) {
+    l2_flush_kernel<<<148 * 8, 256, 0, s>>>(reinterpret_cast<uint4*>(buf), bytes / 16);
+    return cudaGetLastError();
+}
+
+}  // namespace fdr

@@ -1,0 +1,95 @@
+// passes.h -- host-visible argument blocks and launchers of the fused FFT passes.
+//
+// The restoration of one pair of real planes (a, b) packed as z = a + i*b is
+//   pass 1  rows  : load a,b (f32 or u8), zero-pad, FFT along x           -> spectrum S1
+//   pass 2  cols  : FFT along y, multiply by the Wiener factor
+//                   Wf = conj(H)/(|H|^2+K), inverse FFT along y            (in place)
+//   pass 3  rows  : inverse FFT along x, split Re -> plane a, Im -> plane b,
+//                   min/max of every padded plane                          -> raw planes
+//   pass 4        : min-max normalise + crop + 8-bit pack (or f32 planes)
+// which replaces the reference's 12 launches per channel
+// (/root/reference/fft/fft_gpu.cu:338-368).  Packing two real planes into one complex
+// transform is valid because Wf is the spectrum of a real kernel (Hermitian), so
+// IFFT(Wf * FFT(a + i b)) = a' + i b'.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fdr {
+
+enum RowInMode { ROW_IN_PAIR_F32 = 0, ROW_IN_PAIR_U8 = 1, ROW_IN_COMPLEX = 2 };
+enum RowOutMode { ROW_OUT_COMPLEX = 0, ROW_OUT_REAL_PAIR = 1 };
+enum ColMode { COL_FFT = 0, COL_WIENER = 1, COL_MAKE_WIENER = 2, COL_FILTER = 3 };
+
+struct RowPassArgs {
+    int n;               // transform length (padded columns), power of two
+    int nrows;           // rows transformed per pair (grid.x covers them)
+    int npairs;          // grid.y
+    int in_mode, out_mode;
+    int conj_in, conj_out;  // complex modes: conjugate on load / on store (inverse = conj FFT conj)
+    // ---- real-pair input (pass 1) ----
+    const float* in_f32;         // planar f32: unit u at in_f32 + u*in_unit_stride, row stride in_row_stride
+    long long in_unit_stride;
+    long long in_row_stride;
+    const uint8_t* in_u8;        // interleaved u8 [img][H][W][C]; unit u = img*C + c
+    int channels;                // C
+    int img_rows, img_cols;      // H, W of the unpadded image: x >= W reads 0
+    long long unit_base;         // global index of local unit 0
+    long long units_total;       // global unit count (a pair's second unit may not exist)
+    // ---- complex input / output ----
+    const float2* cin;           // pair p at cin + p*cplane, row r at + r*n
+    float2* cout;
+    long long cplane;
+    // ---- real-pair output (pass 3) ----
+    float* raw;                  // local unit u at raw + u*raw_unit_stride, cropped rows x cols
+    long long raw_unit_stride;
+    int raw_rows, raw_cols;      // H, W : only y < H, x < W is stored
+    unsigned int* minmax;        // [local unit][2] ordered-uint encoded min, max over the PADDED plane
+    int local_units;             // units in this chunk
+};
+
+struct ColPassArgs {
+    int n;                // transform length (padded rows), power of two
+    int pitch;            // elements per row (padded columns)
+    int npairs;           // grid.y
+    int mode;             // ColMode
+    int conj_in, conj_out;
+    int rows_valid;       // rows >= rows_valid are read as zero (pass 1 skipped them)
+    float2* data;         // in place; pair p at data + p*cplane
+    long long cplane;
+    const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
+    float2* wiener_out;   // COL_MAKE_WIENER
+    float K;
+};
+
+// Launchers (defined in passes_*.cu).  Return cudaGetLastError() of the launch.
+cudaError_t launch_row_pass(const RowPassArgs& a, cudaStream_t s);
+cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s);
+// One-time: raise the dynamic shared-memory limit of every instantiated kernel.
+cudaError_t configure_pass_kernels();
+// Tile width (columns per CTA) the column pass uses for length n.
+int col_pass_tile_width(int n);
+
+// ---- small kernels (kernels_misc.cu) ----
+struct PsfAffine {  // inverse rotation, computed on the host in double (utils.hpp:20 + warpAffine)
+    double a00, a01, b0, a10, a11, b1;
+};
+cudaError_t launch_motion_psf(float* psf, int size, PsfAffine m, cudaStream_t s);
+cudaError_t launch_minmax_reset(unsigned int* minmax, int units, cudaStream_t s);
+// scale_shift[u] = {scale, shift} as floats from the double-precision min/max rule
+cudaError_t launch_minmax_finalize(const unsigned int* minmax, float2* scale_shift, float* minmax_f32, int units,
+                                   cudaStream_t s);
+// u8 interleaved [img][H][W][C] from raw planes of local units img*C + c
+cudaError_t launch_pack_u8(const float* raw, long long raw_unit_stride, const float2* scale_shift, uint8_t* out,
+                           int imgs, int channels, int rows, int cols, cudaStream_t s);
+// normalised f32 planes [unit][H][W]
+cudaError_t launch_normalize_f32(const float* raw, long long raw_unit_stride, const float2* scale_shift, float* out,
+                                 long long out_unit_stride, int units, int rows, int cols, cudaStream_t s);
+cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, int rows, int cols,
+                            cudaStream_t s);
+// out-of-place batched O(n^2) DFT: element i of batch b at in[b*batch_stride + i*elem_stride]
+cudaError_t launch_dft_naive(const float2* in, float2* out, int n, long long elem_stride, int batch,
+                             long long batch_stride, int inverse, cudaStream_t s);
+cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t s);
+
+}  // namespace fdr

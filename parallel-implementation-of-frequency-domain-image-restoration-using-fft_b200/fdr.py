@@ -1,0 +1,254 @@
+"""ctypes binding of lib/libfdr_b200.so (the C ABI in include/fdr_b200.h).
+
+Test / benchmark harness only: the product's host side is the C++ in fft/ and gpu.cpp.
+The binding never computes anything itself and has NO fallback: if the shared library is
+missing or a call fails, it raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libfdr_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "fdr_b200.h")
+
+_fp = C.POINTER(C.c_float)
+_u8p = C.POINTER(C.c_uint8)
+
+
+class FdrError(RuntimeError):
+    pass
+
+
+def build(jobs=8, quiet=True):
+    """Compile the CUDA library (and the ./gpu CLI) for sm_100a with the package Makefile."""
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.run(["make", "-C", HERE, "-j%d" % jobs, "all"], check=True, env=env,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FdrError("CUDA library not built: %s (run `make -C %s`)" % (LIB_PATH, HERE))
+        L = C.CDLL(LIB_PATH)
+        L.fdr_last_error.restype = C.c_char_p
+        vp, i, f, d, sz, ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_longlong
+        pp = C.POINTER(C.c_void_p)
+        sig = {
+            "fdr_version": [],
+            "fdr_device_count": [C.POINTER(i)],
+            "fdr_host_alloc": [pp, sz],
+            "fdr_host_free": [vp],
+            "fdr_plan_create": [pp, i, i, i, i, i],
+            "fdr_plan_destroy": [vp],
+            "fdr_plan_padded_size": [vp, C.POINTER(i), C.POINTER(i)],
+            "fdr_plan_set_chunk_images": [vp, i],
+            "fdr_plan_set_psf_host": [vp, _fp, i, i, sz, f],
+            "fdr_plan_set_psf_motion": [vp, i, d, f],
+            "fdr_plan_get_psf_host": [vp, _fp, i, C.POINTER(i), C.POINTER(i)],
+            "fdr_plan_get_wiener_host": [vp, _fp],
+            "fdr_restore_planes_host_f32": [vp, C.POINTER(_fp), sz, C.POINTER(_fp), sz, i],
+            "fdr_restore_images_host_u8": [vp, vp, vp, i],
+            "fdr_restore_images_device_u8": [vp, vp, vp, i, vp],
+            "fdr_restore_planes_device_f32": [vp, vp, vp, vp, i, vp],
+            "fdr_plan_last_minmax_host": [vp, _fp, i],
+            "fdr_plan_get_profile": [vp, _fp],
+            "fdr_plan_last_launch_count": [vp, C.POINTER(ll)],
+            "fdr_plan_forward_spectrum_host": [vp, _fp, sz, _fp],
+            "fdr_plan_filtered_spectrum_host": [vp, _fp, sz, _fp],
+            "fdr_dft2d_host": [_fp, i, i, i],
+            "fdr_fft_radix2_host": [_fp, i, i],
+            "fdr_dft_naive_host": [_fp, i, i],
+            "fdr_transform_rows_host": [_fp, i, i, i],
+            "fdr_synth_images_device_u8": [vp, C.c_uint32, ll, i, i, i, i, vp],
+            "fdr_l2_flush_device": [vp, sz, vp],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return [s for s in dir(lib()) if s.startswith("fdr_")]
+
+
+def _check(rc):
+    if rc != 0:
+        raise FdrError("fdr error %d: %s" % (rc, lib().fdr_last_error().decode()))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t=_fp):
+    return a.ctypes.data_as(t)
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().fdr_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = C.c_void_p()
+        _check(lib().fdr_host_alloc(C.byref(self.ptr), self.nbytes))
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().fdr_host_free(self.ptr)
+            self.ptr = None
+
+
+class Plan:
+    """One image geometry (rows x cols x channels) + one PSF/K: mirrors what
+    fft_gpu::wienerDeblur_RGB_optimized sets up per call (fft_gpu.cu:279-322)."""
+
+    def __init__(self, rows, cols, channels=3, max_images=1, device=0):
+        self.h = C.c_void_p()
+        self.rows, self.cols, self.channels = rows, cols, channels
+        _check(lib().fdr_plan_create(C.byref(self.h), rows, cols, channels, max_images, device))
+        pr, pc = C.c_int(), C.c_int()
+        _check(lib().fdr_plan_padded_size(self.h, C.byref(pr), C.byref(pc)))
+        self.padded = (pr.value, pc.value)
+
+    def close(self):
+        if self.h:
+            lib().fdr_plan_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_chunk_images(self, n):
+        _check(lib().fdr_plan_set_chunk_images(self.h, n))
+
+    def set_psf(self, psf, K=0.01):
+        psf = _f32(psf)
+        _check(lib().fdr_plan_set_psf_host(self.h, _p(psf), psf.shape[0], psf.shape[1], 0, K))
+
+    def set_psf_motion(self, length, angle, K=0.01):
+        _check(lib().fdr_plan_set_psf_motion(self.h, int(length), float(angle), K))
+
+    def get_psf(self):
+        r, c = C.c_int(), C.c_int()
+        _check(lib().fdr_plan_get_psf_host(self.h, None, 0, C.byref(r), C.byref(c)))
+        out = np.empty((r.value, c.value), np.float32)
+        _check(lib().fdr_plan_get_psf_host(self.h, _p(out), out.size, C.byref(r), C.byref(c)))
+        return out
+
+    def get_wiener(self):
+        out = np.empty(self.padded, np.complex64)
+        _check(lib().fdr_plan_get_wiener_host(self.h, _p(out.view(np.float32))))
+        return out
+
+    def restore_planes(self, planes):
+        """list of (rows, cols) f32 planes -> list of normalised f32 planes (host API)."""
+        ins = [_f32(p) for p in planes]
+        outs = [np.empty((self.rows, self.cols), np.float32) for _ in ins]
+        n = len(ins)
+        ip = (_fp * n)(*[_p(a) for a in ins])
+        op = (_fp * n)(*[_p(a) for a in outs])
+        _check(lib().fdr_restore_planes_host_f32(self.h, ip, 0, op, 0, n))
+        return outs
+
+    def restore_images_u8(self, images, out=None):
+        """u8 (n, rows, cols, channels) -> u8 restored images (host API).  `images`/`out` may be
+        PinnedArray.array views to skip the staging copy."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        n = images.shape[0]
+        assert images.shape[1:] == (self.rows, self.cols, self.channels), images.shape
+        if out is None:
+            out = np.empty_like(images)
+        _check(lib().fdr_restore_images_host_u8(self.h, images.ctypes.data, out.ctypes.data, n))
+        return out
+
+    def restore_images_device_u8(self, d_in, d_out, n_images, stream=0):
+        _check(lib().fdr_restore_images_device_u8(self.h, d_in, d_out, n_images, stream))
+
+    def restore_planes_device_f32(self, d_in, d_out_f32, d_out_u8, n_planes, stream=0):
+        _check(lib().fdr_restore_planes_device_f32(self.h, d_in, d_out_f32, d_out_u8, n_planes, stream))
+
+    def last_minmax(self, n_planes):
+        out = np.zeros((n_planes, 2), np.float32)
+        _check(lib().fdr_plan_last_minmax_host(self.h, _p(out), n_planes))
+        return out
+
+    def profile(self):
+        out = np.zeros(6, np.float32)
+        _check(lib().fdr_plan_get_profile(self.h, _p(out)))
+        return out
+
+    def last_launch_count(self):
+        n = C.c_longlong(0)
+        _check(lib().fdr_plan_last_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def forward_spectrum(self, plane):
+        plane = _f32(plane)
+        out = np.empty(self.padded, np.complex64)
+        _check(lib().fdr_plan_forward_spectrum_host(self.h, _p(plane), 0, _p(out.view(np.float32))))
+        return out
+
+    def filtered_spectrum(self, plane):
+        plane = _f32(plane)
+        out = np.empty(self.padded, np.complex64)
+        _check(lib().fdr_plan_filtered_spectrum_host(self.h, _p(plane), 0, _p(out.view(np.float32))))
+        return out
+
+
+def dft2d(m, inverse=False):
+    a = np.ascontiguousarray(m, dtype=np.complex64).copy()
+    _check(lib().fdr_dft2d_host(_p(a.view(np.float32)), a.shape[0], a.shape[1], int(inverse)))
+    return a
+
+
+def fft_radix2(x, inverse=False):
+    a = np.ascontiguousarray(x, dtype=np.complex64).copy()
+    _check(lib().fdr_fft_radix2_host(_p(a.view(np.float32)), a.shape[0], int(inverse)))
+    return a
+
+
+def dft_naive(x, inverse=False):
+    a = np.ascontiguousarray(x, dtype=np.complex64).copy()
+    _check(lib().fdr_dft_naive_host(_p(a.view(np.float32)), a.shape[0], int(inverse)))
+    return a
+
+
+def transform_rows(m, inverse=False):
+    a = np.ascontiguousarray(m, dtype=np.complex64).copy()
+    _check(lib().fdr_transform_rows_host(_p(a.view(np.float32)), a.shape[0], a.shape[1], int(inverse)))
+    return a
+
+
+def synth_images_device_u8(d_out, seed, first_image, n_images, channels, rows, cols, stream=0):
+    _check(lib().fdr_synth_images_device_u8(d_out, seed, first_image, n_images, channels, rows, cols, stream))
+
+
+def l2_flush(d_scratch, nbytes, stream=0):
+    _check(lib().fdr_l2_flush_device(d_scratch, nbytes, stream))
