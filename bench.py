@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixel/s deblurred (FFT -> Wiener -> IFFT -> normalise -> 8-bit pack).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code
+
+One "step" restores one batch of synthetic 8-bit BGR images (default workload = BASELINE.json
+configs[3]: 256 x 2048x2048x3, counter-hash pixels, psf 50/30, K = 0.01).  Inputs are resident in
+HBM before the timed region; `value` is whole-job Mpixel/s (max time over ranks); `e2e` is the
+same metric through the host-buffer C-ABI call (pinned host -> device -> pinned host inside the
+timed region).  Rank 0 prints ONE JSON line.  Multi-GPU: independent image batches per rank, no
+data-path collective (weak scaling).  torch is used only for device memory, streams, events and
+torch.distributed plumbing; every kernel is ours (lib/libfdr_b200.so via ctypes).
+"""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "parallel-implementation-of-frequency-domain-image-restoration-using-fft_b200")
+
+WORKLOADS = {
+    # name: (config_index, images, H, W, psf_len, psf_angle)
+    "batch256x2048": (3, 256, 2048, 2048, 50, 30.0),
+    "rgb4096": (2, 1, 4096, 4096, 50, 30.0),
+    "rgb16384": (4, 1, 16384, 16384, 50, 30.0),
+    "car": (1, 1, 330, 640, 40, 45.0),
+    "cat": (0, 1, 782, 1920, 50, 30.0),
+}
+K_WIENER = 0.01
+CONTRACT_BYTES_PER_CHANNEL_PIXEL = 53.0
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_restore_images(O, mode, cfg_idx, first, count, H, W, psf, threads):
+    """Reference CPU path on `count` synthetic images: serial.cpp:33-39 loop per image."""
+    ref = O.ref() if O.have_ref() else None
+    import numpy as np
+    if ref is not None and mode == "openmp":
+        ref.set_threads(threads)
+    t_total = 0.0
+    for i in range(first, first + count):
+        img = O.synth_image_u8(cfg_idx, i, H, W)
+        planes = [O.pad_pow2(img[c].astype(np.float32) * np.float32(1.0 / 255.0)) for c in range(3)]
+        t0 = time.perf_counter()
+        for pl in planes:
+            if ref is not None:
+                ref.wiener(pl, psf, K_WIENER, mode)
+            else:
+                O.port().wiener_deblur(pl, psf, K_WIENER)
+        t_total += time.perf_counter() - t0
+    return t_total
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, compiled unmodified
+    from the reference sources; openmp mode with every host thread), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+    cfg_idx, images, H, W, plen, pang = WORKLOADS[args.workload]
+    psf = O.port().motion_psf(plen, pang)
+    have_ref = O.have_ref()
+    threads = os.cpu_count() or 1
+    mode = "openmp" if have_ref else "serial"
+    sample = max(1, min(images, args.ref_images))
+    for _ in range(args.warmup):
+        cpu_restore_images(O, mode, cfg_idx, 0, 1, H, W, psf, threads)
+    t = 0.0
+    for s in range(args.steps):
+        t += cpu_restore_images(O, mode, cfg_idx, s * sample, sample, H, W, psf, threads)
+    mpx = sample * H * W * args.steps / t / 1e6
+    line = {
+        "impl": "reference", "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
+        "value": mpx, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "images_per_step_sample": sample, "image": [H, W, 3], "psf": [plen, pang],
+                   "K": K_WIENER},
+        "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": threads if mode == "openmp" else 1,
+                         "kind": "reference" if have_ref else "port",
+                         "sample": "%d image(s) of %dx%dx3 per step, reference %s mode (fft_%s.cpp compiled unmodified)"
+                                   % (sample, H, W, mode, mode)},
+        "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="batch256x2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--images", type=int, default=0, help="images per rank per step (0 = the workload's own count)")
+    ap.add_argument("--chunk-images", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-images", type=int, default=2, help="--impl reference: images per step")
+    ap.add_argument("--cpu-sample-images", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--flush-l2", action="store_true", help="overwrite a 512 MB scratch between steps (small workloads)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    fdr = _load("fdr_b200_binding", os.path.join(PKG, "fdr.py"))
+
+    cfg_idx, images, H, W, plen, pang = WORKLOADS[args.workload]
+    B = args.images or images
+    seed = 0xF17E0000 + cfg_idx
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(device=dev)  # explicit non-default stream: kernels, events and copies all on it
+    torch.cuda.set_stream(stream)
+    sh = stream.cuda_stream
+
+    plan = fdr.Plan(H, W, 3, max_images=B, device=local_rank)
+    if args.chunk_images:
+        plan.set_chunk_images(args.chunk_images)
+    plan.set_psf_motion(plen, pang, K_WIENER)  # PSF built on the device
+    d_in = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    d_out = torch.empty_like(d_in)
+    first_image = rank * B  # each rank restores its own images (weak scaling, no collective)
+    fdr.synth_images_device_u8(d_in.data_ptr(), seed, first_image, B, 3, H, W, sh)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
+    torch.cuda.synchronize()
+
+    def step():
+        if flush is not None:
+            fdr.l2_flush(flush.data_ptr(), flush.numel(), sh)
+        plan.restore_images_device_u8(d_in.data_ptr(), d_out.data_ptr(), B, sh)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region: device-resident throughput, CUDA events on the launching stream ----
+    plan.set_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches_per_step = plan.last_launch_count()
+    ktimes = plan.kernel_timing()
+    plan.set_kernel_timing(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    px_per_step = B * H * W * world
+    value = px_per_step * args.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory both ways) ----
+    e2e = None
+    if not args.no_e2e:
+        hin = fdr.PinnedArray((B, H, W, 3), np.uint8)
+        hout = fdr.PinnedArray((B, H, W, 3), np.uint8)
+        d_in_cpu = d_in.cpu().numpy()
+        np.copyto(hin.array, d_in_cpu)
+        del d_in_cpu
+        plan.restore_images_u8(hin.array, hout.array)  # warm-up (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            plan.restore_images_u8(hin.array, hout.array)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": px_per_step * args.e2e_steps / float(tt.item()) / 1e6, "unit": "Mpixel/s",
+               "h2d_bytes_per_step": int(hin.nbytes), "d2h_bytes_per_step": int(hout.nbytes),
+               "steps": args.e2e_steps, "ms_per_step": float(tt.item()) / args.e2e_steps * 1e3}
+        e2e_first = hout.array[0].copy()
+        hin.free()
+        hout.free()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (live CUDA-event durations of this run) ----
+    peak, peak_src = measured_peak_gbs()
+    dom = max(ktimes, key=lambda k: ktimes[k]["ms"])
+    kd = ktimes[dom]
+    achieved = kd["bytes"] / (kd["ms"] * 1e-3) / 1e9 if kd["ms"] > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    ksum = sum(v["ms"] for v in ktimes.values())
+    form_bytes = sum(v["bytes"] for v in ktimes.values())
+    chan_px = B * H * W * 3 * args.steps
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
+        "bytes_per_launch": kd["bytes"] / max(kd["launches"], 1), "ms_per_launch": kd["ms"] / max(kd["launches"], 1),
+        "kernel_share_of_step": kd["ms"] / ksum if ksum else None,
+        "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                        "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0)} for k, v in ktimes.items()},
+        "pipeline": {
+            "formulation_bytes_per_channel_pixel": form_bytes / chan_px,
+            "contract_bytes_per_channel_pixel": CONTRACT_BYTES_PER_CHANNEL_PIXEL,
+            "GBps_formulation": form_bytes / (ms_max * 1e-3) / 1e9,
+            "frac_of_peak_formulation": form_bytes / (ms_max * 1e-3) / 1e9 / peak,
+            "GBps_contract53": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (ms_max * 1e-3) / 1e9,
+            "frac_of_peak_contract53": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (ms_max * 1e-3) / 1e9 / peak,
+        },
+    }
+
+    # ---- parity spot check + CPU baseline on a bounded sample (rank 0 only) ----
+    O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+    psf = O.port().motion_psf(plen, pang)
+    parity = None
+    cpu_baseline = None
+    want_cpu = (not args.no_cpu_baseline) and world == 1
+    if want_cpu or not args.no_check:
+        n_s = max(1, min(B, args.cpu_sample_images)) if want_cpu else 1
+        mode = "serial"
+        t_cpu = 0.0
+        got0 = d_out[0].cpu().numpy()
+        worst = [0, 0, 0]
+        for i in range(n_s):
+            img = O.synth_image_u8(cfg_idx, first_image + i, H, W)
+            planes = [img[c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(3)]
+            t0 = time.perf_counter()
+            if O.have_ref():
+                outs = [O.ref().wiener(O.pad_pow2(pl), psf, K_WIENER, mode)[:H, :W] for pl in planes]
+            else:
+                outs = [O.port().wiener_deblur(O.pad_pow2(pl), psf, K_WIENER)["norm"][:H, :W] for pl in planes]
+            t_cpu += time.perf_counter() - t0
+            if i == 0 and not args.no_check:
+                want = np.stack([O.port().pack_u8(o) for o in outs], -1)
+                d = np.abs(got0.astype(np.int16) - want.astype(np.int16))
+                worst = [int((d == 0).sum()), int((d == 1).sum()), int((d > 1).sum())]
+                parity = {"image": first_image, "pixels": int(d.size), "exact": worst[0], "off_by_1": worst[1],
+                          "off_by_more": worst[2], "frac_within_1": float((d <= 1).mean()),
+                          "e2e_matches_device": bool(e2e is None or np.array_equal(e2e_first, got0))}
+        if want_cpu:
+            cpu_baseline = {"value": n_s * H * W / t_cpu / 1e6, "unit": "Mpixel/s", "cores": 1,
+                            "kind": "reference" if O.have_ref() else "port",
+                            "sample": "%d image(s) of %dx%dx3, reference serial mode (fft_serial.cpp compiled unmodified), %d host cores present"
+                                      % (n_s, H, W, os.cpu_count() or 0)}
+
+    line = {
+        "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
+        "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "images_per_gpu_per_step": B, "image": [H, W, 3], "psf": [plen, pang],
+                   "K": K_WIENER, "input": "u8 BGR interleaved, counter-hash (SURVEY 8d), resident in HBM",
+                   "output": "u8 BGR interleaved", "l2": "flush between steps" if flush is not None else
+                   "working set (%.1f GB in + out per step) larger than L2" % (2 * B * H * W * 3 / 1e9),
+                   "parallelism": "images sharded across ranks, no collective" if world > 1 else "single GPU",
+                   "chunk_images": args.chunk_images or "auto"},
+        "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

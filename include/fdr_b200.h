@@ -97,6 +97,13 @@ int fdr_plan_last_minmax_host(fdr_plan* plan, float* minmax, int capacity_planes
 /* Six buckets in ms of the most recent HOST restore call, in the order of the reference's
  * Profiler (fft_gpu.cu:17-57): alloc, H2D, pre-process, compute, D2H, post-process. */
 int fdr_plan_get_profile(const fdr_plan* plan, float ms[6]);
+/* Per-kernel device timing.  When enabled every pass launch is bracketed by a CUDA event pair
+ * on the launching stream.  get_kernel_timing drains the records accumulated since the last
+ * call: for kind 0 = pass 1 (rows forward), 1 = pass 2 (columns + Wiener), 2 = pass 3 (rows
+ * inverse + min/max), 3 = pass 4 (normalise/pack) it returns the summed duration in ms, the
+ * launch count and the summed algorithmic bytes (this formulation's own count). */
+int fdr_plan_set_kernel_timing(fdr_plan* plan, int enabled);
+int fdr_plan_get_kernel_timing(fdr_plan* plan, double total_ms[4], long long launches[4], double bytes[4]);
 /* Number of kernels the most recent restore call launched. */
 int fdr_plan_last_launch_count(const fdr_plan* plan, long long* launches);
 

@@ -53,14 +53,8 @@ int next_pow2(int n) {  // utils.hpp:27-31
 }
 bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
-bool g_kernels_configured[64] = {false};
-
 int ensure_device(int device) {
     FDR_CUDA(cudaSetDevice(device));
-    if (device >= 0 && device < 64 && !g_kernels_configured[device]) {
-        FDR_CUDA(configure_pass_kernels());
-        g_kernels_configured[device] = true;
-    }
     return FDR_OK;
 }
 
@@ -133,6 +127,8 @@ struct fdr_plan {
     DevBuf<float> mmf;            // chunk units x 2
     DevBuf<float2> wiener;        // Rp x Cp
     DevBuf<float> psf;            // psf_rows x psf_cols
+    const float2* tw_rows = nullptr;  // twiddles for length Cp (row passes)
+    const float2* tw_cols = nullptr;  // twiddles for length Rp (column passes)
     // staging for the host entry points
     DevBuf<uint8_t> d_in_u8, d_out_u8;
     DevBuf<float> d_in_f32, d_out_f32;
@@ -141,6 +137,15 @@ struct fdr_plan {
     float profile_ms[6] = {0, 0, 0, 0, 0, 0};
     long long launches = 0;
     int last_units = 0;
+    // optional per-kernel timing (event pair around every pass launch)
+    bool ktiming = false;
+    struct KRec {
+        int kind;
+        cudaEvent_t a, b;
+        double bytes;
+    };
+    std::vector<KRec> krecs;
+    std::vector<cudaEvent_t> ev_pool;
 
     size_t plane_elems() const { return (size_t)Rp * Cp; }
     // images per chunk: keep the complex workspace of a chunk near 96 MB (inside the 126 MB L2)
@@ -168,6 +173,37 @@ struct InputDesc {
     const float* f32 = nullptr;
     long long unit_stride = 0, row_stride = 0;
     const uint8_t* u8 = nullptr;
+};
+
+struct KernelTimer {  // records an event pair around one launch when kernel timing is on
+    fdr_plan* p;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kind;
+    double bytes;
+    static cudaEvent_t get(fdr_plan* p) {
+        if (!p->ev_pool.empty()) {
+            cudaEvent_t e = p->ev_pool.back();
+            p->ev_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    KernelTimer(fdr_plan* p_, cudaStream_t s_, int kind_, double bytes_) : p(p_), s(s_), kind(kind_), bytes(bytes_) {
+        if (p->ktiming) {
+            a = get(p);
+            b = get(p);
+            cudaEventRecord(a, s);
+        }
+    }
+    ~KernelTimer() {
+        if (p->ktiming) {
+            cudaEventRecord(b, s);
+            p->krecs.push_back({kind, a, b, bytes});
+        }
+    }
 };
 
 int ensure_workspace(fdr_plan* p, int chunk_units) {
@@ -216,7 +252,13 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r1.units_total = n_units;
         r1.cout = p->spec.p;
         r1.cplane = (long long)p->plane_elems();
-        FDR_CUDA(launch_row_pass(r1, s));
+        r1.tw = p->tw_rows;
+        const double px_in = (double)p->H * p->W * (in.mode == ROW_IN_PAIR_U8 ? 1.0 : 4.0) * nu;
+        const double P = (double)p->plane_elems();
+        {
+            KernelTimer kt(p, s, 0, px_in + 8.0 * p->H * p->Cp * np);
+            FDR_CUDA(launch_row_pass(r1, s));
+        }
 
         ColPassArgs c2{};
         c2.n = p->Rp;
@@ -228,7 +270,11 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         c2.cplane = (long long)p->plane_elems();
         c2.wiener = p->wiener.p;
         c2.K = p->K;
-        FDR_CUDA(launch_col_pass(c2, s));
+        c2.tw = p->tw_cols;
+        {
+            KernelTimer kt(p, s, 1, (8.0 * p->H * p->Cp + 16.0 * P) * np);
+            FDR_CUDA(launch_col_pass(c2, s));
+        }
 
         RowPassArgs r3{};
         r3.n = p->Cp;
@@ -246,15 +292,21 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r3.raw_cols = p->W;
         r3.minmax = p->mm.p;
         r3.local_units = nu;
-        FDR_CUDA(launch_row_pass(r3, s));
+        r3.tw = p->tw_rows;
+        {
+            KernelTimer kt(p, s, 2, 8.0 * P * np + 4.0 * HW * nu);
+            FDR_CUDA(launch_row_pass(r3, s));
+        }
 
         FDR_CUDA(launch_minmax_finalize(p->mm.p, p->ss.p, p->mmf.p, nu, s));
         p->launches += 5;
         if (out_u8) {
+            KernelTimer kt(p, s, 3, 5.0 * HW * nu);
             FDR_CUDA(launch_pack_u8(p->raw.p, HW, p->ss.p, out_u8 + base * HW, nu / C, C, p->H, p->W, s));
             p->launches += 1;
         }
         if (out_f32) {
+            KernelTimer kt(p, s, 3, 8.0 * HW * nu);
             FDR_CUDA(launch_normalize_f32(p->raw.p, HW, p->ss.p, out_f32 + base * HW, HW, nu, p->H, p->W, s));
             p->launches += 1;
         }
@@ -285,6 +337,7 @@ int build_wiener(fdr_plan* p) {
     r.units_total = 1;
     r.cout = p->spec.p;
     r.cplane = (long long)p->plane_elems();
+    r.tw = p->tw_rows;
     FDR_CUDA(launch_row_pass(r, s));
     ColPassArgs c{};
     c.n = p->Rp;
@@ -296,6 +349,7 @@ int build_wiener(fdr_plan* p) {
     c.cplane = (long long)p->plane_elems();
     c.wiener_out = p->wiener.p;
     c.K = p->K;
+    c.tw = p->tw_cols;
     FDR_CUDA(launch_col_pass(c, s));
     FDR_CUDA(cudaStreamSynchronize(s));
     p->have_wiener = true;
@@ -390,11 +444,13 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
     p->max_images = max_images;
     p->Rp = next_pow2(rows);
     p->Cp = next_pow2(cols);
-    cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+    cudaError_t e = get_twiddles(p->Cp, &p->tw_rows);
+    if (e == cudaSuccess) e = get_twiddles(p->Rp, &p->tw_cols);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&p->ev[i]);
     if (e != cudaSuccess) {
         delete p;
-        return set_error(FDR_E_CUDA, "plan stream/event creation: %s", cudaGetErrorString(e));
+        return set_error(FDR_E_CUDA, "plan twiddle/stream/event creation: %s", cudaGetErrorString(e));
     }
     *plan = p;
     return FDR_OK;
@@ -421,6 +477,11 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
     p->h_f32_out.release();
     for (int i = 0; i < 8; ++i)
         if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    for (auto& r : p->krecs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : p->ev_pool) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return FDR_OK;
@@ -624,6 +685,34 @@ __attribute__((visibility("default"))) int fdr_plan_last_launch_count(const fdr_
     return FDR_OK;
 }
 
+__attribute__((visibility("default"))) int fdr_plan_set_kernel_timing(fdr_plan* p, int enabled) {
+    if (!p) return set_error(FDR_E_INVALID, "plan is NULL");
+    p->ktiming = enabled != 0;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_get_kernel_timing(fdr_plan* p, double total_ms[4], long long launches[4], double bytes[4]) {
+    if (!p || !total_ms || !launches || !bytes) return set_error(FDR_E_INVALID, "bad arguments");
+    for (int i = 0; i < 4; ++i) {
+        total_ms[i] = 0;
+        launches[i] = 0;
+        bytes[i] = 0;
+    }
+    FDR_CUDA(cudaSetDevice(p->device));
+    for (auto& r : p->krecs) {
+        FDR_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        FDR_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        total_ms[r.kind] += ms;
+        launches[r.kind] += 1;
+        bytes[r.kind] += r.bytes;
+        p->ev_pool.push_back(r.a);
+        p->ev_pool.push_back(r.b);
+    }
+    p->krecs.clear();
+    return FDR_OK;
+}
+
 static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* out, int col_mode) {
     if (!p || !plane || !out) return set_error(FDR_E_INVALID, "bad arguments");
     if (col_mode == COL_FILTER && !p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
@@ -649,6 +738,7 @@ static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* 
     r.units_total = 1;
     r.cout = p->spec.p;
     r.cplane = (long long)p->plane_elems();
+    r.tw = p->tw_rows;
     FDR_CUDA(launch_row_pass(r, s));
     ColPassArgs c{};
     c.n = p->Rp;
@@ -659,6 +749,7 @@ static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* 
     c.data = p->spec.p;
     c.cplane = (long long)p->plane_elems();
     c.wiener = p->wiener.p;
+    c.tw = p->tw_cols;
     FDR_CUDA(launch_col_pass(c, s));
     FDR_CUDA(cudaMemcpyAsync(out, p->spec.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost, s));
     FDR_CUDA(cudaStreamSynchronize(s));
@@ -683,7 +774,8 @@ static int rows_device(float2* d, float2* tmp, int rows, int n, int inverse, cud
         r.npairs = 1;
         r.in_mode = ROW_IN_COMPLEX;
         r.out_mode = ROW_OUT_COMPLEX;
-        r.conj_in = r.conj_out = inverse ? 1 : 0;
+        r.conj = inverse ? 1 : 0;
+        FDR_CUDA(get_twiddles(n, &r.tw));
         r.cin = d;
         r.cout = d;
         r.cplane = (long long)rows * n;
@@ -702,7 +794,8 @@ static int cols_device(float2* d, float2* tmp, int rows, int cols, int inverse, 
         c.pitch = cols;
         c.npairs = 1;
         c.mode = COL_FFT;
-        c.conj_in = c.conj_out = inverse ? 1 : 0;
+        c.conj = inverse ? 1 : 0;
+        FDR_CUDA(get_twiddles(rows, &c.tw));
         c.rows_valid = rows;
         c.data = d;
         c.cplane = (long long)rows * cols;

@@ -6,13 +6,16 @@
 // result is in natural order (Stockham autosort, no bit reversal).  Between stages
 // the points are exchanged through shared memory; each stage is one radix-16 (or
 // the remaining 8/4/2) DFT done entirely in registers with compile-time inner
-// twiddles and one sincospi per thread for the outer twiddle.
+// twiddles.  Outer twiddles come from a per-length table laid out [stage][b][r][t]
+// (one coalesced 8-byte load each, L1-resident), computed once per device in double
+// precision -- no sincos or power products in the hot loop.
 //
-// Shared-memory layout of an exchange (split re/im planes, CW interleaved
-// transforms):  word(idx, c) = ((idx ^ ((idx >> 4) & (32/CW - 1))) * CW + c).
-// For E = 16 this is bank-conflict free for the scattered stage writes and the
-// strided reads at every N and every CW in {1,2,4,8,16,32} (simulated offline,
-// see DESIGN.md).
+// Shared-memory layout of an exchange: float2 words, CW interleaved transforms,
+//   word(idx, c) = (idx ^ ((idx >> 4) & (16/CW - 1))) * CW + c.
+// For E = 16 this is bank-conflict free (64-bit accesses, half-warp phases) for the
+// scattered stage writes and the strided reads at every N and every CW (simulated
+// offline).  The XOR swizzle is linear over GF(2), so every access is
+// addr0 ^ compile-time-constant: one LOP3 per 8-byte LDS/STS.
 //
 // Only the FORWARD transform (e^{-2 pi i nk/N}) is implemented; callers obtain the
 // inverse as conj(FFT(conj(x))), folding the conjugations into their load/store.
@@ -30,9 +33,6 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.y, b.x, a.x * b.y));
-}
-__device__ __forceinline__ float2 csqr(float2 a) {
-    return make_float2(fmaf(a.x, a.x, -(a.y * a.y)), (a.x + a.x) * a.y);
 }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // a * (-i)
@@ -123,59 +123,58 @@ template <> struct Dft<16> {
     }
 };
 
-// x[r] *= w^r, r = 1..R-1, powers built by a product tree of depth <= 4.
-template <int R> __device__ __forceinline__ void apply_twiddle_powers(float2* x, float2 w) {
-    if constexpr (R >= 2) x[1] = cmul(x[1], w);
-    if constexpr (R >= 4) {
-        float2 w2 = csqr(w);
-        float2 w3 = cmul(w2, w);
-        x[2] = cmul(x[2], w2);
-        x[3] = cmul(x[3], w3);
-        if constexpr (R >= 8) {
-            float2 w4 = csqr(w2);
-            x[4] = cmul(x[4], w4);
-            x[5] = cmul(x[5], cmul(w4, w));
-            x[6] = cmul(x[6], cmul(w4, w2));
-            x[7] = cmul(x[7], cmul(w4, w3));
-            if constexpr (R >= 16) {
-                float2 w8 = csqr(w4);
-                float2 w12 = cmul(w8, w4);
-                x[8] = cmul(x[8], w8);
-                x[9] = cmul(x[9], cmul(w8, w));
-                x[10] = cmul(x[10], cmul(w8, w2));
-                x[11] = cmul(x[11], cmul(w8, w3));
-                x[12] = cmul(x[12], w12);
-                x[13] = cmul(x[13], cmul(w12, w));
-                x[14] = cmul(x[14], cmul(w12, w2));
-                x[15] = cmul(x[15], cmul(w12, w3));
-            }
-        }
-    }
-}
-
 template <int N> struct FftGeom {
     static constexpr int E = (N >= 16) ? 16 : N;  // points per thread
     static constexpr int T = N / E;               // threads per transform
 };
 
-template <int CW> __device__ __forceinline__ int smem_word(int idx, int c) {
-    constexpr int G = 32 / CW;
-    return ((idx ^ ((idx >> 4) & (G - 1))) * CW) + c;
-}
+// ---------------------------------------------------------------------------------
+// Twiddle table of one length N: for every stage after the first, for every butterfly
+// b of the thread and every r = 1..R-1, T entries  exp(-2 pi i * r * k / (NS*R)),
+// k = (t + b*T) mod NS.  Offsets are compile-time.
+// ---------------------------------------------------------------------------------
+template <int N, int NS> struct TwStage {
+    static constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T;
+    static constexpr int REM = N / NS;
+    static constexpr int R = (REM < E) ? REM : E;
+    static constexpr int NB = E / R;
+    static constexpr int ENTRIES = (NS > 1) ? NB * (R - 1) * T : 0;
+    // table offset of this stage = entries of all earlier stages
+};
+// All stages before the last have radix 16 (greedy radices), so the stage with sub-length NS is
+// preceded by the stages with sub-lengths NS/16, NS/256, ...
+template <int N, int NS, bool FIRST = (NS <= 16)> struct TwOffset {
+    static constexpr int value = TwOffset<N, NS / 16>::value + TwStage<N, NS / 16>::ENTRIES;
+};
+template <int N, int NS> struct TwOffset<N, NS, true> {
+    static constexpr int value = 0;
+};
+// Total entries for length N (stages have NS = 1, E, E^2, ... while NS < N).
+template <int N, int NS = 1> struct TwTotal {
+    static constexpr int R = TwStage<N, NS>::R;
+    static constexpr int value = TwStage<N, NS>::ENTRIES + ((NS * R < N) ? TwTotal<N, (NS * R < N) ? NS * R : N>::value : 0);
+};
+template <int N> struct TwTotal<N, N> {
+    static constexpr int value = 0;
+};
+
+template <int CW> struct Swz {
+    static constexpr int G = (CW >= 16) ? 1 : 16 / CW;
+    __host__ __device__ static constexpr int f(int idx) { return idx ^ ((idx >> 4) & (G - 1)); }
+};
 
 // One Stockham stage of radix R with sub-transform length NS already done.
-template <int N, int R, int NS> __device__ __forceinline__ void stage_butterflies(float2* v, int t) {
-    constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T, NB = E / R, L = NS * R;
+template <int N, int R, int NS> __device__ __forceinline__ void stage_butterflies(float2* v, const float2* __restrict__ tw, int t) {
+    constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T, NB = E / R;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         float2 x[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) x[r] = v[b + r * NB];
         if constexpr (NS > 1) {
-            const int k = (t + b * T) & (NS - 1);
-            float s, c;
-            sincospif((float)k * (2.0f / (float)L), &s, &c);
-            apply_twiddle_powers<R>(x, make_float2(c, -s));
+            const float2* twb = tw + TwOffset<N, NS>::value + b * (R - 1) * T + t;
+#pragma unroll
+            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(twb + (r - 1) * T));
         }
         Dft<R>::run(x);
 #pragma unroll
@@ -184,39 +183,34 @@ template <int N, int R, int NS> __device__ __forceinline__ void stage_butterflie
 }
 
 // Scatter the stage outputs to shared memory and gather the next stage's inputs.
-// sre/sim: this CTA's exchange planes (N*CW floats each); c = transform index in the tile.
-template <int N, int CW, int R, int NS>
-__device__ __forceinline__ void stage_exchange(float2* v, float* sre, float* sim, int t, int c) {
+// ex: this CTA's exchange buffer (N*CW float2); c = transform index in the tile.
+template <int N, int CW, int R, int NS> __device__ __forceinline__ void stage_exchange(float2* v, float2* ex, int t, int c) {
     constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T, NB = E / R;
+    char* exb = reinterpret_cast<char*>(ex);
     __syncthreads();
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int j = t + b * T;
         const int base = ((j & ~(NS - 1)) * R) + (j & (NS - 1));
+        const int a0 = (Swz<CW>::f(base) * CW + c) * 8;
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int w = smem_word<CW>(base + q * NS, c);
-            sre[w] = v[b + q * NB].x;
-            sim[w] = v[b + q * NB].y;
-        }
+        for (int q = 0; q < R; ++q) *reinterpret_cast<float2*>(exb + (a0 ^ (Swz<CW>::f(q * NS) * CW * 8))) = v[b + q * NB];
     }
     __syncthreads();
+    const int r0 = (Swz<CW>::f(t) * CW + c) * 8;
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const int w = smem_word<CW>(t + T * m, c);
-        v[m] = make_float2(sre[w], sim[w]);
-    }
+    for (int m = 0; m < E; ++m) v[m] = *reinterpret_cast<const float2*>(exb + (r0 ^ (Swz<CW>::f(T * m) * CW * 8)));
 }
 
 template <int N, int CW, int NS> struct FftStages {
-    __device__ __forceinline__ static void run(float2* v, float* sre, float* sim, int t, int c) {
+    __device__ __forceinline__ static void run(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c) {
         constexpr int E = FftGeom<N>::E;
         constexpr int REM = N / NS;
         constexpr int R = (REM < E) ? REM : E;
-        stage_butterflies<N, R, NS>(v, t);
+        stage_butterflies<N, R, NS>(v, tw, t);
         if constexpr (NS * R < N) {
-            stage_exchange<N, CW, R, NS>(v, sre, sim, t, c);
-            FftStages<N, CW, NS * R>::run(v, sre, sim, t, c);
+            stage_exchange<N, CW, R, NS>(v, ex, t, c);
+            FftStages<N, CW, NS * R>::run(v, ex, tw, t, c);
         }
     }
 };
@@ -224,13 +218,33 @@ template <int N, int CW, int NS> struct FftStages {
 // Forward FFT of length N over the E points held by thread t (points t + T*m).
 // All T*CW threads of all transforms in the CTA must call this together when N > E
 // (it contains __syncthreads).
-template <int N, int CW> __device__ __forceinline__ void fft_forward(float2* v, float* sre, float* sim, int t, int c) {
-    if constexpr (N > 1) FftStages<N, CW, 1>::run(v, sre, sim, t, c);
+template <int N, int CW> __device__ __forceinline__ void fft_forward(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c) {
+    if constexpr (N > 1) FftStages<N, CW, 1>::run(v, ex, tw, t, c);
 }
 
 // Shared memory (bytes) one CTA needs for `ntransforms` interleaved transforms of length N.
 template <int N> constexpr size_t fft_smem_bytes(int ntransforms) {
-    return (N > FftGeom<N>::E) ? (size_t)2 * N * ntransforms * sizeof(float) : 0;
+    return (N > FftGeom<N>::E) ? (size_t)N * ntransforms * sizeof(float2) : 0;
+}
+
+// Fills the twiddle table of length N (TwTotal<N>::value entries), double precision.
+template <int N, int NS> __device__ __forceinline__ void tw_fill_stage(float2* tw, int i) {
+    using St = TwStage<N, NS>;
+    constexpr int T = St::T, R = St::R;
+    if constexpr (NS > 1) {
+        if (i < St::ENTRIES) {
+            const int t = i % T, rr = (i / T) % (R - 1), b = i / (T * (R - 1));
+            const int k = (t + b * T) & (NS - 1);
+            double s, c;
+            sincospi(2.0 * (double)((rr + 1) * k) / (double)(NS * R), &s, &c);
+            tw[TwOffset<N, NS>::value + i] = make_float2((float)c, (float)(-s));
+        }
+    }
+    if constexpr (NS * R < N) tw_fill_stage<N, NS * R>(tw, i);
+}
+template <int N> __global__ void tw_fill_kernel(float2* tw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (N > 16) tw_fill_stage<N, 1>(tw, i);
 }
 
 }  // namespace fdr

@@ -26,7 +26,8 @@ struct RowPassArgs {
     int nrows;           // rows transformed per pair (grid.x covers them)
     int npairs;          // grid.y
     int in_mode, out_mode;
-    int conj_in, conj_out;  // complex modes: conjugate on load / on store (inverse = conj FFT conj)
+    int conj;            // complex->complex only: conjugate on load and on store (inverse = conj FFT conj)
+    const float2* tw;    // twiddle table of length n (get_twiddles)
     // ---- real-pair input (pass 1) ----
     const float* in_f32;         // planar f32: unit u at in_f32 + u*in_unit_stride, row stride in_row_stride
     long long in_unit_stride;
@@ -53,7 +54,8 @@ struct ColPassArgs {
     int pitch;            // elements per row (padded columns)
     int npairs;           // grid.y
     int mode;             // ColMode
-    int conj_in, conj_out;
+    int conj;             // COL_FFT only: inverse transform
+    const float2* tw;     // twiddle table of length n
     int rows_valid;       // rows >= rows_valid are read as zero (pass 1 skipped them)
     float2* data;         // in place; pair p at data + p*cplane
     long long cplane;
@@ -65,8 +67,8 @@ struct ColPassArgs {
 // Launchers (defined in passes_*.cu).  Return cudaGetLastError() of the launch.
 cudaError_t launch_row_pass(const RowPassArgs& a, cudaStream_t s);
 cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s);
-// One-time: raise the dynamic shared-memory limit of every instantiated kernel.
-cudaError_t configure_pass_kernels();
+// Twiddle table for power-of-two length n on the current device (cached).
+cudaError_t get_twiddles(int n, const float2** out);
 // Tile width (columns per CTA) the column pass uses for length n.
 int col_pass_tile_width(int n);
 

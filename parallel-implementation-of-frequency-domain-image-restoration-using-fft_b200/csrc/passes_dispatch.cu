@@ -1,11 +1,16 @@
-// passes_dispatch.cu -- run-time length -> instantiated kernel.
+// passes_dispatch.cu -- run-time length -> instantiated kernel, and the per-device twiddle tables.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "passes.h"
 
 namespace fdr {
 #define X(LOGN)                                                              \
     cudaError_t launch_row_pass_##LOGN(const RowPassArgs&, cudaStream_t);    \
     cudaError_t launch_col_pass_##LOGN(const ColPassArgs&, cudaStream_t);    \
-    cudaError_t configure_pass_##LOGN();
+    cudaError_t tw_fill_##LOGN(float2*, cudaStream_t);                       \
+    int tw_total_##LOGN();
 #define FDR_ALL_LOGNS X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14)
 FDR_ALL_LOGNS
 #undef X
@@ -37,13 +42,46 @@ cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s) {
     return cudaErrorInvalidValue;
 }
 
-cudaError_t configure_pass_kernels() {
-    cudaError_t e;
-#define X(LOGN)                  \
-    e = configure_pass_##LOGN(); \
+// Twiddle table of length n on the current device: built once (double-precision sincospi on the
+// device), cached for the life of the process.
+cudaError_t get_twiddles(int n, const float2** out) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, float2*> cache;
+    *out = nullptr;
+    const int l = ilog2_exact(n);
+    if (l < 0 || l > 14) return cudaErrorInvalidValue;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    FDR_ALL_LOGNS
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, l});
+    if (it != cache.end()) {
+        *out = it->second;
+        return cudaSuccess;
+    }
+    int total = 0;
+    switch (l) {
+#define X(LOGN) \
+    case LOGN: total = tw_total_##LOGN(); break;
+        FDR_ALL_LOGNS
 #undef X
+    }
+    float2* p = nullptr;
+    e = cudaMalloc(&p, sizeof(float2) * (size_t)(total > 0 ? total : 1));
+    if (e != cudaSuccess) return e;
+    switch (l) {
+#define X(LOGN) \
+    case LOGN: e = tw_fill_##LOGN(p, 0); break;
+        FDR_ALL_LOGNS
+#undef X
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return e;
+    }
+    cache[{dev, l}] = p;
+    *out = p;
     return cudaSuccess;
 }
 

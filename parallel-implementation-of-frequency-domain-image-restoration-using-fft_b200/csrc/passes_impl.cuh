@@ -25,76 +25,77 @@ template <int LOGN> struct RowGeom {
     static constexpr size_t SMEM = fft_smem_bytes<N>(RPC);
 };
 
-template <int LOGN>
+template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
 __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const RowPassArgs a) {
     using Gm = RowGeom<LOGN>;
     constexpr int N = Gm::N, E = Gm::E, T = Gm::T, RPC = Gm::RPC;
-    extern __shared__ float smem[];
+    extern __shared__ float2 smem2[];
     const int tid = threadIdx.x;
     const int rl = (RPC > 1) ? (tid / T) : 0;
     const int t = (RPC > 1) ? (tid % T) : tid;
     const int row = blockIdx.x * RPC + rl;
     const int pair = blockIdx.y;
     const bool active = row < a.nrows;
-    float* sre = smem + (size_t)rl * 2 * N;
-    float* sim = sre + N;
+    float2* ex = smem2 + (size_t)rl * N;
 
     const long long u0 = 2LL * pair, u1 = u0 + 1;  // local units
     const bool has1 = (a.unit_base + u1) < a.units_total;
 
     float2 v[E];
-    if (a.in_mode == ROW_IN_COMPLEX) {
-        const float2* src = a.cin + (long long)pair * a.cplane + (long long)row * N;
+    if constexpr (IN_MODE == ROW_IN_COMPLEX) {
+        const float2* src = a.cin + (long long)pair * a.cplane + (long long)row * N + t;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             float2 z = make_float2(0.f, 0.f);
-            if (active) z = src[t + T * m];
-            if (a.conj_in) z.y = -z.y;
+            if (active) z = src[T * m];
+            if constexpr (CONJ) z.y = -z.y;
             v[m] = z;
         }
-    } else if (a.in_mode == ROW_IN_PAIR_F32) {
+    } else if constexpr (IN_MODE == ROW_IN_PAIR_F32) {
         const float* p0 = a.in_f32 + (a.unit_base + u0) * a.in_unit_stride + (long long)row * a.in_row_stride;
-        const float* p1 = a.in_f32 + (a.unit_base + u1) * a.in_unit_stride + (long long)row * a.in_row_stride;
+        const float* p1 = has1 ? a.in_f32 + (a.unit_base + u1) * a.in_unit_stride + (long long)row * a.in_row_stride : p0;
+        const float k1 = has1 ? 1.f : 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int x = t + T * m;
             float2 z = make_float2(0.f, 0.f);
             if (active && x < a.img_cols) {
                 z.x = __ldg(p0 + x);
-                if (has1) z.y = __ldg(p1 + x);
+                z.y = __ldg(p1 + x) * k1;
             }
             v[m] = z;
         }
     } else {  // ROW_IN_PAIR_U8 : x * (float)(1/255.)  (serial.cpp:24-25 convertTo + /= 255.0)
-        const long long g0 = a.unit_base + u0, g1 = a.unit_base + u1;
+        const long long g0 = a.unit_base + u0, g1 = has1 ? a.unit_base + u1 : g0;
         const int C = a.channels;
         const long long i0 = g0 / C, i1 = g1 / C;
         const int c0 = (int)(g0 - i0 * C), c1 = (int)(g1 - i1 * C);
         const uint8_t* p0 = a.in_u8 + ((i0 * a.img_rows + row) * (long long)a.img_cols) * C + c0;
         const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row) * (long long)a.img_cols) * C + c1;
         const float inv255 = (float)(1.0 / 255.0);
+        const float k1 = has1 ? inv255 : 0.f;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int x = t + T * m;
             float2 z = make_float2(0.f, 0.f);
             if (active && x < a.img_cols) {
-                z.x = (float)__ldg(p0 + (long long)x * C) * inv255;
-                if (has1) z.y = (float)__ldg(p1 + (long long)x * C) * inv255;
+                z.x = (float)__ldg(p0 + x * C) * inv255;
+                z.y = (float)__ldg(p1 + x * C) * k1;
             }
             v[m] = z;
         }
     }
 
-    fft_forward<N, 1>(v, sre, sim, t, 0);
+    fft_forward<N, 1>(v, ex, a.tw, t, 0);
 
-    if (a.out_mode == ROW_OUT_COMPLEX) {
+    if constexpr (OUT_MODE == ROW_OUT_COMPLEX) {
         if (active) {
-            float2* dst = a.cout + (long long)pair * a.cplane + (long long)row * N;
+            float2* dst = a.cout + (long long)pair * a.cplane + (long long)row * N + t;
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 float2 z = v[m];
-                if (a.conj_out) z.y = -z.y;
-                dst[t + T * m] = z;
+                if constexpr (CONJ) z.y = -z.y;
+                dst[T * m] = z;
             }
         }
     } else {
@@ -102,20 +103,23 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
         // pair is conj(v): plane a = v.x, plane b = -v.y.
         float mn0 = INFINITY, mx0 = -INFINITY, mn1 = INFINITY, mx1 = -INFINITY;
         if (active) {
-            const bool store_row = row < a.raw_rows;
-            float* d0 = a.raw + u0 * a.raw_unit_stride + (long long)row * a.raw_cols;
-            float* d1 = a.raw + u1 * a.raw_unit_stride + (long long)row * a.raw_cols;
 #pragma unroll
             for (int m = 0; m < E; ++m) {
-                const int x = t + T * m;
-                const float ra = v[m].x, rb = -v[m].y;
-                mn0 = fminf(mn0, ra);
-                mx0 = fmaxf(mx0, ra);
-                mn1 = fminf(mn1, rb);
-                mx1 = fmaxf(mx1, rb);
-                if (store_row && x < a.raw_cols) {
-                    d0[x] = ra;
-                    if (has1) d1[x] = rb;
+                v[m].y = -v[m].y;
+                mn0 = fminf(mn0, v[m].x);
+                mx0 = fmaxf(mx0, v[m].x);
+                mn1 = fminf(mn1, v[m].y);
+                mx1 = fmaxf(mx1, v[m].y);
+            }
+            if (row < a.raw_rows) {
+                float* d0 = a.raw + u0 * a.raw_unit_stride + (long long)row * a.raw_cols + t;
+                float* d1 = a.raw + u1 * a.raw_unit_stride + (long long)row * a.raw_cols + t;
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    if (t + T * m < a.raw_cols) {
+                        d0[T * m] = v[m].x;
+                        if (has1) d1[T * m] = v[m].y;
+                    }
                 }
             }
         }
@@ -178,95 +182,137 @@ template <int LOGN, int CW> struct ColGeom {
     static constexpr size_t SMEM = fft_smem_bytes<N>(CW);
 };
 
-template <int LOGN, int CW>
-__global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS) col_pass_kernel(const ColPassArgs a) {
+template <int LOGN, int CW, int MODE, bool CONJ>
+__global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>::THREADS <= 512 && MODE == COL_WIENER) ? 1024 / ColGeom<LOGN, CW>::THREADS : 1) col_pass_kernel(const ColPassArgs a) {
     using Gm = ColGeom<LOGN, CW>;
     constexpr int N = Gm::N, E = Gm::E, T = Gm::T;
-    extern __shared__ float smem[];
-    float* sre = smem;
-    float* sim = smem + (size_t)N * CW;
+    extern __shared__ float2 smem2[];
+    float2* ex = smem2;
     const int tid = threadIdx.x;
     const int c = tid % CW, t = tid / CW;
     const int col = blockIdx.x * CW + c;
     const bool active = col < a.pitch;
-    float2* base = a.data + (long long)blockIdx.y * a.cplane + col;
+    const long long stride = (long long)T * a.pitch;
+    float2* base = a.data + (long long)blockIdx.y * a.cplane + (long long)t * a.pitch + col;
 
     float2 v[E];
 #pragma unroll
     for (int m = 0; m < E; ++m) {
-        const int r = t + T * m;
         float2 z = make_float2(0.f, 0.f);
-        if (active && r < a.rows_valid) z = base[(long long)r * a.pitch];
-        if (a.conj_in) z.y = -z.y;
+        if (active && t + T * m < a.rows_valid) z = base[m * stride];
+        if constexpr (CONJ) z.y = -z.y;
         v[m] = z;
     }
 
-    fft_forward<N, CW>(v, sre, sim, t, c);
+    fft_forward<N, CW>(v, ex, a.tw, t, c);
 
-    if (a.mode == COL_WIENER) {
-        const float2* wf = a.wiener + col;
+    if constexpr (MODE == COL_WIENER) {
+        const float2* wf = a.wiener + (long long)t * a.pitch + col;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            const int r = t + T * m;
             float2 w = make_float2(0.f, 0.f);
-            if (active) w = __ldg(wf + (long long)r * a.pitch);
+            if (active) w = __ldg(wf + m * stride);
             const float2 y = cmul(v[m], w);
             v[m] = make_float2(y.x, -y.y);
         }
-        fft_forward<N, CW>(v, sre, sim, t, c);
+        fft_forward<N, CW>(v, ex, a.tw, t, c);
     }
-
-    if (a.mode == COL_FILTER) {
-        const float2* wf = a.wiener + col;
+    if constexpr (MODE == COL_FILTER) {
+        const float2* wf = a.wiener + (long long)t * a.pitch + col;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             float2 w = make_float2(0.f, 0.f);
-            if (active) w = __ldg(wf + (long long)(t + T * m) * a.pitch);
+            if (active) w = __ldg(wf + m * stride);
             v[m] = cmul(v[m], w);
         }
     }
 
     if (!active) return;
-    if (a.mode == COL_MAKE_WIENER) {
-        float2* wo = a.wiener_out + col;
+    if constexpr (MODE == COL_MAKE_WIENER) {
+        float2* wo = a.wiener_out + (long long)t * a.pitch + col;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            const int r = t + T * m;
             const float hr = v[m].x, hi = v[m].y;
             const float denom = fmaf(hr, hr, hi * hi) + a.K;  // fft_serial.cpp:195-197
-            wo[(long long)r * a.pitch] = make_float2(hr / denom, -hi / denom);
+            wo[m * stride] = make_float2(hr / denom, -hi / denom);
         }
     } else {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            const int r = t + T * m;
             float2 z = v[m];
-            if (a.conj_out) z.y = -z.y;
-            base[(long long)r * a.pitch] = z;
+            if constexpr (CONJ) z.y = -z.y;
+            base[m * stride] = z;
         }
     }
 }
 
-template <int LOGN> cudaError_t launch_row_pass_t(const RowPassArgs& a, cudaStream_t s) {
+template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row_variant(const RowPassArgs& a, cudaStream_t s) {
     using Gm = RowGeom<LOGN>;
+    if (Gm::SMEM > 48 * 1024) {
+        static unsigned long long configured = 0;  // bit per device ordinal
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!(configured >> (dev & 63) & 1ULL)) {
+            cudaError_t e = cudaFuncSetAttribute(row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+            if (e != cudaSuccess) return e;
+            configured |= 1ULL << (dev & 63);
+        }
+    }
     dim3 grid((a.nrows + Gm::RPC - 1) / Gm::RPC, a.npairs);
-    row_pass_kernel<LOGN><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
+    row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
     return cudaGetLastError();
 }
-template <int LOGN> cudaError_t configure_row_pass_t() {
-    return cudaFuncSetAttribute(row_pass_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)RowGeom<LOGN>::SMEM);
+
+template <int LOGN> cudaError_t launch_row_pass_t(const RowPassArgs& a, cudaStream_t s) {
+    if (a.in_mode == ROW_IN_PAIR_U8 && a.out_mode == ROW_OUT_COMPLEX) return launch_row_variant<LOGN, ROW_IN_PAIR_U8, ROW_OUT_COMPLEX, false>(a, s);
+    if (a.in_mode == ROW_IN_PAIR_F32 && a.out_mode == ROW_OUT_COMPLEX) return launch_row_variant<LOGN, ROW_IN_PAIR_F32, ROW_OUT_COMPLEX, false>(a, s);
+    if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_REAL_PAIR) return launch_row_variant<LOGN, ROW_IN_COMPLEX, ROW_OUT_REAL_PAIR, false>(a, s);
+    if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_COMPLEX && !a.conj)
+        return launch_row_variant<LOGN, ROW_IN_COMPLEX, ROW_OUT_COMPLEX, false>(a, s);
+    if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_COMPLEX && a.conj)
+        return launch_row_variant<LOGN, ROW_IN_COMPLEX, ROW_OUT_COMPLEX, true>(a, s);
+    return cudaErrorInvalidValue;
 }
-template <int LOGN, int CW> cudaError_t launch_col_pass_t(const ColPassArgs& a, cudaStream_t s) {
+
+template <int LOGN, int CW, int MODE, bool CONJ> cudaError_t launch_col_variant(const ColPassArgs& a, cudaStream_t s) {
     using Gm = ColGeom<LOGN, CW>;
+    if (Gm::SMEM > 48 * 1024) {
+        static unsigned long long configured = 0;  // bit per device ordinal
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!(configured >> (dev & 63) & 1ULL)) {
+            cudaError_t e = cudaFuncSetAttribute(col_pass_kernel<LOGN, CW, MODE, CONJ>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+            if (e != cudaSuccess) return e;
+            configured |= 1ULL << (dev & 63);
+        }
+    }
     dim3 grid((a.pitch + CW - 1) / CW, a.npairs);
-    col_pass_kernel<LOGN, CW><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
+    col_pass_kernel<LOGN, CW, MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
     return cudaGetLastError();
 }
-template <int LOGN, int CW> cudaError_t configure_col_pass_t() {
-    return cudaFuncSetAttribute(col_pass_kernel<LOGN, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)ColGeom<LOGN, CW>::SMEM);
+
+template <int LOGN, int CW> cudaError_t launch_col_pass_t(const ColPassArgs& a, cudaStream_t s) {
+    switch (a.mode) {
+        case COL_FFT:
+            return a.conj ? launch_col_variant<LOGN, CW, COL_FFT, true>(a, s) : launch_col_variant<LOGN, CW, COL_FFT, false>(a, s);
+        case COL_WIENER: return launch_col_variant<LOGN, CW, COL_WIENER, false>(a, s);
+        case COL_MAKE_WIENER: return launch_col_variant<LOGN, CW, COL_MAKE_WIENER, false>(a, s);
+        case COL_FILTER: return launch_col_variant<LOGN, CW, COL_FILTER, false>(a, s);
+    }
+    return cudaErrorInvalidValue;
 }
+
+template <int LOGN> cudaError_t tw_fill_t(float2* tw, cudaStream_t s) {
+    constexpr int N = 1 << LOGN;
+    constexpr int total = TwTotal<N>::value;
+    if (total == 0) return cudaSuccess;
+    constexpr int per_stage_max = 15 * FftGeom<N>::T;
+    tw_fill_kernel<N><<<(per_stage_max + 255) / 256, 256, 0, s>>>(tw);
+    return cudaGetLastError();
+}
+template <int LOGN> constexpr int tw_total_t() { return TwTotal<(1 << LOGN)>::value; }
 
 // Default tile width per length: keep T*CW <= 512 threads, CW*8 B >= 32 B where possible.
 constexpr int default_col_cw(int logn) {

@@ -63,6 +63,8 @@ def lib():
             "fdr_plan_last_minmax_host": [vp, _fp, i],
             "fdr_plan_get_profile": [vp, _fp],
             "fdr_plan_last_launch_count": [vp, C.POINTER(ll)],
+            "fdr_plan_set_kernel_timing": [vp, i],
+            "fdr_plan_get_kernel_timing": [vp, C.POINTER(d), C.POINTER(ll), C.POINTER(d)],
             "fdr_plan_forward_spectrum_host": [vp, _fp, sz, _fp],
             "fdr_plan_filtered_spectrum_host": [vp, _fp, sz, _fp],
             "fdr_dft2d_host": [_fp, i, i, i],
@@ -208,6 +210,18 @@ class Plan:
         n = C.c_longlong(0)
         _check(lib().fdr_plan_last_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def set_kernel_timing(self, on=True):
+        _check(lib().fdr_plan_set_kernel_timing(self.h, int(on)))
+
+    KERNEL_KINDS = ("pass1_rows_fwd", "pass2_cols_wiener", "pass3_rows_inv_minmax", "pass4_normalize_pack")
+
+    def kernel_timing(self):
+        ms = (C.c_double * 4)()
+        n = (C.c_longlong * 4)()
+        b = (C.c_double * 4)()
+        _check(lib().fdr_plan_get_kernel_timing(self.h, ms, n, b))
+        return {k: {"ms": ms[i], "launches": n[i], "bytes": b[i]} for i, k in enumerate(self.KERNEL_KINDS)}
 
     def forward_spectrum(self, plane):
         plane = _f32(plane)
