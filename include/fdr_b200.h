@@ -128,6 +128,10 @@ int fdr_dft_naive_host(float* interleaved, int n, int inverse);
  * two, naive DFT otherwise (fft_serial.cpp:90-108).  `rows` independent rows. */
 int fdr_transform_rows_host(float* interleaved, int rows, int n, int inverse);
 
+/* motionBlurKernel(size, angle) (utils.hpp:15-24): length x length fp32 PSF built on the device
+ * (current CUDA device) and copied to psf_out.  Bit-identical to OpenCV 4.x warpAffine. */
+int fdr_motion_psf_host(int length, double angle_deg, float* psf_out);
+
 /* ---- synthetic input + measurement helpers (bench, tests) ----------------------------- */
 /* Counter-hash u8 images generated on the device, identical to oracle/orc_synth_u8. */
 int fdr_synth_images_device_u8(void* d_out_images, uint32_t seed, long long first_image, int n_images, int channels,

@@ -301,8 +301,12 @@ inline void normalize(const Mat& src, Mat& dst, double alpha, double beta, int n
         }
     }
     const double dmin = std::min(alpha, beta), dmax = std::max(alpha, beta);
-    const double scale = (dmax - dmin) * ((smax - smin) > DBL_EPSILON ? 1. / (smax - smin) : 0.);
-    const double shift = dmin - smin * scale;
+    // OpenCV 4.x, rtype == CV_32F: scale is rounded to float BEFORE the shift is derived
+    // (scale = (float)scale; shift = (float)dmin - (float)(smin*scale)); checked against
+    // cv2.normalize on 300 random planes and tests/golden/normalize_case.npz.
+    double scale = (dmax - dmin) * ((smax - smin) > DBL_EPSILON ? 1. / (smax - smin) : 0.);
+    scale = (double)(float)scale;
+    const double shift = (double)((float)dmin - (float)(smin * scale));
     const float a = (float)scale, b = (float)shift;
     Mat out(src.rows, src.cols, CV_32F);
     for (int r = 0; r < src.rows; ++r) {

@@ -151,8 +151,8 @@ void orc_wiener(float* G, const float* H, size_t n, float K) {
 }
 
 /* ---- fft_serial.cpp:246  normalize(NORM_MINMAX, 0, 1) ---------------------------
- * min/max as double, scale = 1/(max-min) (0 if the range <= DBL_EPSILON),
- * shift = -min*scale, applied as fmaf(x, (float)scale, (float)shift) -- cv2 4.13 fuses the
+ * min/max as double, scale = (float)(1/(max-min)) (0 if the range <= DBL_EPSILON),
+ * shift = -(float)(min*scale), applied as fmaf(x, scale, shift) -- cv2 4.13 fuses the
  * multiply-add (pinned by tests/golden/normalize_*.npy).  In place.
  * mm[0], mm[1] receive min and max when mm != NULL. */
 void orc_normalize_minmax(float* x, size_t n, double* mm) {
@@ -162,9 +162,11 @@ void orc_normalize_minmax(float* x, size_t n, double* mm) {
         if (v < smin) smin = v;
         if (v > smax) smax = v;
     }
+    /* OpenCV 4.x with a CV_32F destination rounds scale to float before deriving the shift:
+     * scale = (float)scale; shift = (float)dmin - (float)(smin*scale)  (pinned against cv2 4.13) */
     double scale = (smax - smin) > DBL_EPSILON ? 1. / (smax - smin) : 0.;
-    double shift = 0.0 - smin * scale;
-    float a = (float)scale, b = (float)shift;
+    float a = (float)scale;
+    float b = 0.0f - (float)(smin * (double)a);
     for (size_t i = 0; i < n; ++i) x[i] = fmaf(x[i], a, b);
     if (mm) {
         mm[0] = smin;

@@ -862,6 +862,17 @@ __attribute__((visibility("default"))) int fdr_dft_naive_host(float* data, int n
 
 __attribute__((visibility("default"))) int fdr_transform_rows_host(float* data, int rows, int n, int inverse) { return transform_host(data, rows, n, inverse, true, false); }
 
+__attribute__((visibility("default"))) int fdr_motion_psf_host(int length, double angle_deg, float* psf_out) {
+    if (length < 1 || !psf_out) return set_error(FDR_E_INVALID, "bad PSF arguments");
+    float* d = nullptr;
+    FDR_CUDA(cudaMalloc(&d, sizeof(float) * (size_t)length * length));
+    cudaError_t e = launch_motion_psf(d, length, motion_affine(length, angle_deg), 0);
+    if (e == cudaSuccess) e = cudaMemcpy(psf_out, d, sizeof(float) * (size_t)length * length, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_error(FDR_E_CUDA, "motion PSF: %s", cudaGetErrorString(e));
+    return FDR_OK;
+}
+
 __attribute__((visibility("default"))) int fdr_synth_images_device_u8(void* d_out, uint32_t seed, long long first_image, int n_images, int channels, int rows,
                                int cols, void* stream) {
     if (!d_out || n_images < 0 || channels < 1 || rows < 1 || cols < 1) return set_error(FDR_E_INVALID, "bad arguments");

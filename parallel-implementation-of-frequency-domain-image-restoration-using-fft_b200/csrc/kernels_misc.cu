@@ -67,16 +67,18 @@ __device__ __forceinline__ float f32_from_ordered(unsigned int u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-// cv::normalize(NORM_MINMAX, 0, 1) (fft_serial.cpp:246): scale = 1/(max-min) in double
-// (0 when the range <= DBL_EPSILON), shift = -min*scale, both then rounded to float.
+// cv::normalize(NORM_MINMAX, 0, 1) (fft_serial.cpp:246) as OpenCV 4.x evaluates it for a CV_32F
+// destination: scale = (float)(1/(max-min)) (0 when the range <= DBL_EPSILON), shift =
+// -(float)(min*scale) with the product in double; applied as one fused multiply-add.
 __global__ void minmax_finalize_kernel(const unsigned int* mm, float2* ss, float* mmf, int units) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= units) return;
     const double smin = (double)f32_from_ordered(mm[2 * i]);
     const double smax = (double)f32_from_ordered(mm[2 * i + 1]);
     const double scale = (smax - smin) > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0;
-    const double shift = 0.0 - smin * scale;
-    ss[i] = make_float2((float)scale, (float)shift);
+    const float a = (float)scale;
+    const float b = 0.0f - (float)__dmul_rn(smin, (double)a);
+    ss[i] = make_float2(a, b);
     if (mmf) {
         mmf[2 * i] = (float)smin;
         mmf[2 * i + 1] = (float)smax;

@@ -71,6 +71,7 @@ def lib():
             "fdr_fft_radix2_host": [_fp, i, i],
             "fdr_dft_naive_host": [_fp, i, i],
             "fdr_transform_rows_host": [_fp, i, i, i],
+            "fdr_motion_psf_host": [i, d, _fp],
             "fdr_synth_images_device_u8": [vp, C.c_uint32, ll, i, i, i, i, vp],
             "fdr_l2_flush_device": [vp, sz, vp],
         }
@@ -258,6 +259,13 @@ def transform_rows(m, inverse=False):
     a = np.ascontiguousarray(m, dtype=np.complex64).copy()
     _check(lib().fdr_transform_rows_host(_p(a.view(np.float32)), a.shape[0], a.shape[1], int(inverse)))
     return a
+
+
+def motion_psf(length, angle):
+    """utils.hpp:15-24 motionBlurKernel, built on the device."""
+    out = np.empty((length, length), np.float32)
+    _check(lib().fdr_motion_psf_host(int(length), float(angle), _p(out)))
+    return out
 
 
 def synth_images_device_u8(d_out, seed, first_image, n_images, channels, rows, cols, stream=0):

@@ -1,0 +1,149 @@
+"""CPU tests (no GPU): pin the oracle.
+
+* the plain-C restatement (oracle/wiener_oracle.c) must reproduce the reference's OWN compiled
+  code (oracle/_ref, unmodified fft_serial.cpp) bit for bit, and the committed golden vectors
+  generated from that code and from cv2 (tests/golden/make_golden.py);
+* nothing here touches the product library.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_l2
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype != np.complex64 else a.view(np.float32).view(np.uint32)
+
+
+def test_psf_matches_cv2_golden(oracle):
+    """utils.hpp:15-24 motionBlurKernel: bit-identical to cv2 4.13 on every stored case."""
+    g = np.load(os.path.join(GOLDEN, "psf_cases.npz"))
+    assert len(g.files) >= 10
+    for key in g.files:
+        _, s, ang = key.split("_")
+        got = oracle.port().motion_psf(int(s), float(ang))
+        assert np.array_equal(bits(got), bits(g[key])), key
+    # SURVEY.md 8(a) a1 known answers
+    p = oracle.port().motion_psf(50, 30.0)
+    assert int((p != 0).sum()) == 101 and abs(float(p.sum()) - 1.00109) < 1e-5 and float(p.max()) == np.float32(0.02)
+    p = oracle.port().motion_psf(40, 45.0)
+    assert int((p != 0).sum()) == 87 and abs(float(p.sum()) - 1.10415) < 1e-5
+    assert hashlib.sha256(oracle.port().motion_psf(50, 30.0).tobytes()).hexdigest().startswith("97848e6b")
+    assert hashlib.sha256(oracle.port().motion_psf(40, 45.0).tobytes()).hexdigest().startswith("c27782b0")
+
+
+def test_normalize_matches_cv2_golden(oracle):
+    g = np.load(os.path.join(GOLDEN, "normalize_case.npz"))
+    x = g["x"].copy()
+    # reuse the port's normalise through a 1-row "restore": call the C function directly
+    import ctypes as C
+    a = np.ascontiguousarray(x.ravel())
+    oracle.port().L.orc_normalize_minmax(a.ctypes.data_as(C.POINTER(C.c_float)), a.size, None)
+    assert np.array_equal(bits(a.reshape(x.shape)), bits(g["y"]))
+
+
+def test_port_matches_reference_goldens(oracle):
+    """fft_serial.cpp:40-68, 71-87, 113-139, 141-261 on the committed vectors (made by the
+    reference's own code)."""
+    g = np.load(os.path.join(GOLDEN, "restore_small.npz"))
+    P = oracle.port()
+    assert np.array_equal(bits(P.fft1d(g["fft64_in"])), bits(g["fft64_fwd"]))
+    assert np.array_equal(bits(P.fft1d(g["fft64_in"], True)), bits(g["fft64_inv"]))
+    assert np.array_equal(bits(P.fft1d(g["dft12_in"])), bits(g["dft12_fwd"]))
+    for name in ("a", "b"):
+        img, psf = g[name + "_img"], g[name + "_psf"]
+        res = P.wiener_deblur(oracle.pad_pow2(img), psf, 0.01, want=("norm", "G"))
+        assert np.array_equal(bits(res["norm"]), bits(g[name + "_norm"])), name
+        assert np.array_equal(bits(res["G"]), bits(g[name + "_G"])), name
+
+
+def test_port_bit_exact_vs_compiled_reference(oracle):
+    """Random inputs through both the C port and oracle/_ref (reference compiled unmodified)."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    P, R = oracle.port(), oracle.ref()
+    rng = np.random.default_rng(7)
+    for n in (1, 2, 8, 64, 512, 4096, 16384):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        for inv in (False, True):
+            assert np.array_equal(bits(P.fft1d(x, inv)), bits(R.fft1d(x, inv))), (n, inv)
+    m = (rng.standard_normal((32, 64)) + 1j * rng.standard_normal((32, 64))).astype(np.complex64)
+    assert np.array_equal(bits(P.dft2d(m)), bits(R.dft2d(m)))
+    assert np.array_equal(bits(P.dft2d(m, True)), bits(R.dft2d(m, True)))
+    for (H, W, S, ang) in ((64, 128, 9, 30.0), (256, 128, 21, 45.0), (8, 8, 3, 10.0)):
+        img = rng.random((H, W), dtype=np.float32)
+        psf = P.motion_psf(S, ang)
+        a = P.wiener_deblur(img, psf, 0.01)["norm"]
+        b = R.wiener(img, psf, 0.01, "serial")
+        assert np.array_equal(bits(a), bits(b)), (H, W)
+        # the reference's other CPU modes agree with serial to fp32 noise (openmp.cpp:12-36: 1e-3)
+        assert np.abs(R.wiener(img, psf, 0.01, "openmp") - b).max() < 1e-5
+        assert np.abs(R.wiener(img, psf, 0.01, "simd") - b).max() < 1e-5
+
+
+def test_oracle_accuracy_against_float64(oracle):
+    """The oracle's own error vs an exact pipeline is ~1e-6..1e-5, far
+    inside the 1e-4 gate, so an accurate-twiddle GPU FFT can meet the gate against it."""
+    P = oracle.port()
+    rng = np.random.default_rng(3)
+    img = rng.random((128, 256), dtype=np.float32)
+    psf = P.motion_psf(15, 30.0)
+    res = P.wiener_deblur(img, psf, 0.01, want=("G", "F", "norm"))
+    G64 = np.fft.fft2(img.astype(np.float64))
+    assert rel_l2(res["G"], G64) < 2e-5
+    hp = np.zeros((128, 256))
+    hp[:15, :15] = psf
+    H64 = np.fft.fft2(hp)
+    F64 = G64 * np.conj(H64) / (np.abs(H64) ** 2 + np.float32(0.01))
+    assert rel_l2(res["F"], F64) < 5e-5
+    f = np.real(np.fft.ifft2(F64)) * img.size
+    n = (f - f.min()) / (f.max() - f.min())
+    assert np.abs(res["norm"] - n).max() < 1e-4
+
+
+def test_sample_image_hashes(oracle):
+    """The port restores the reference's sample images to exactly the bytes the reference's own
+    serial code produced (hashes committed by make_golden.py); channel means are the SURVEY 8(c)
+    sanity values."""
+    cv2 = pytest.importorskip("cv2")
+    hashes = json.load(open(os.path.join(GOLDEN, "sample_hashes.json")))
+    name = "car"  # cat (1024x2048 x3, ~3 s) is covered by the GPU suite
+    h = hashes[name]
+    bgr = cv2.imread(os.path.join(GOLDEN, "input", name + "_blurred.png"), cv2.IMREAD_COLOR)
+    assert hashlib.sha256(bgr.tobytes()).hexdigest() == h["sha256_input_bgr"]
+    planes = [bgr[:, :, c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(3)]
+    psf = oracle.port().motion_psf(*h["psf"])
+    u8, outs = oracle.restore_image_u8(planes, psf, 0.01)
+    assert hashlib.sha256(u8.tobytes()).hexdigest() == h["sha256_u8"]
+    assert np.allclose([o.mean(dtype=np.float64) for o in outs], [0.466985, 0.463748, 0.467249], atol=2e-6)
+
+
+def test_synth_generator_known_answers(oracle):
+    """SURVEY.md 8(d) counter hash, checked against a pure-Python evaluation incl. idx >= 2^32."""
+    def lowbias32(v):
+        v &= 0xFFFFFFFF
+        v ^= v >> 16
+        v = (v * 0x7FEB352D) & 0xFFFFFFFF
+        v ^= v >> 15
+        v = (v * 0x846CA68B) & 0xFFFFFFFF
+        v ^= v >> 16
+        return v
+
+    seed = 0xF17E0003
+    for idx0 in (0, 12345, (1 << 32) - 3, (1 << 33) + 17):
+        got = oracle.port().synth_u8(seed, idx0, 8)
+        want = [lowbias32((i & 0xFFFFFFFF) ^ lowbias32((seed + (i >> 32)) & 0xFFFFFFFF)) >> 24 for i in range(idx0, idx0 + 8)]
+        assert got.tolist() == want
+    big = oracle.port().synth_u8(seed, 0, 1 << 20)
+    assert abs(float(big.mean()) - 127.5) < 0.5
+
+
+def test_pack_u8_round_half_even(oracle):
+    x = np.array([0.0, 0.5 / 255, 1.5 / 255, 2.5 / 255, 1.0, 1.2, -0.3, 0.999], np.float32)
+    want = np.clip(np.rint(x * np.float32(255.0)), 0, 255).astype(np.uint8)
+    assert oracle.port().pack_u8(x).tolist() == want.tolist()
