@@ -128,6 +128,47 @@ int fdr_dft_naive_host(float* interleaved, int n, int inverse);
  * two, naive DFT otherwise (fft_serial.cpp:90-108).  `rows` independent rows. */
 int fdr_transform_rows_host(float* interleaved, int rows, int n, int inverse);
 
+/* ---- one large image row-sharded over several GPUs ------------------------------------- */
+/* Replaces the reference's MPI mode for this path (fft/fft_mpi.cpp:311-470: Bcast dims,
+ * Scatterv rows, [row FFT, MPI_Alltoallv transpose, column FFT, Alltoallv back] x3, Gatherv).
+ * One fdr_shard per GPU (one process per GPU, or several shards in one process).  Rank g owns
+ * padded rows [g*Rp/world, (g+1)*Rp/world) and, in the column pass, padded columns
+ * [g*Cp/world, (g+1)*Cp/world).  The transposes are fused into the row passes as peer (NVLink)
+ * stores and loads; the caller supplies the cross-rank barriers and the 2-float-per-plane
+ * min/max all-reduce (torch.distributed / NCCL), see <package>/fdr_dist.py:
+ *     phase1 | barrier | phase2 | barrier | phase3 | all-reduce(min,max) | phase4            */
+typedef struct fdr_shard fdr_shard;
+int fdr_shard_create(fdr_shard** shard, int rows, int cols, int channels, int rank, int world, int device);
+int fdr_shard_destroy(fdr_shard* shard);
+/* first_row/n_rows: the image rows this rank reads and writes (calculate_distribution,
+ * fft_mpi.cpp:89-100, applied to the padded rows). */
+int fdr_shard_geometry(const fdr_shard* shard, int* first_row, int* n_rows, int* padded_rows, int* padded_cols,
+                       int* cols_per_rank);
+/* This rank's column slab (device pointer) for export to the peers. */
+int fdr_shard_local_slab(const fdr_shard* shard, void** d_slab, size_t* bytes);
+/* CUDA IPC plumbing for one-process-per-GPU runs: 64-byte handles travel through any host
+ * channel (torch.distributed all_gather_object). */
+int fdr_ipc_export(const void* dptr, unsigned char handle[64]);
+int fdr_ipc_open(const unsigned char handle[64], void** dptr);
+int fdr_ipc_close(void* dptr);
+/* slabs[world]: every rank's slab as a pointer valid on THIS device (entry `rank` is ignored). */
+int fdr_shard_set_peers(fdr_shard* shard, void* const* slabs);
+int fdr_shard_set_psf_motion(fdr_shard* shard, int length, double angle_deg, float K);
+int fdr_shard_set_psf_host(fdr_shard* shard, const float* psf, int psf_rows, int psf_cols, float K);
+/* d_in_rows_u8 / d_out_rows_u8: this rank's rows, interleaved 8-bit [n_rows][cols][channels]. */
+int fdr_shard_phase1_rows(fdr_shard* shard, const void* d_in_rows_u8, void* stream);
+int fdr_shard_phase2_cols(fdr_shard* shard, void* stream);
+int fdr_shard_phase3_rows(fdr_shard* shard, void* stream);
+/* [channels][2] floats (min, max of this rank's part of every padded plane) to all-reduce in
+ * place: column 0 with MIN, column 1 with MAX. */
+int fdr_shard_minmax_device(fdr_shard* shard, void** d_minmax_f32);
+int fdr_shard_phase4_pack(fdr_shard* shard, void* d_out_rows_u8, void* stream);
+int fdr_shard_last_launch_count(const fdr_shard* shard, long long* launches);
+/* Rows [first_row, first_row+n_rows) of synthetic image `image` (same stream as
+ * fdr_synth_images_device_u8 for that image). */
+int fdr_synth_rows_device_u8(void* d_out, uint32_t seed, long long image, int channels, int rows_total, int cols,
+                             int first_row, int n_rows, void* stream);
+
 /* motionBlurKernel(size, angle) (utils.hpp:15-24): length x length fp32 PSF built on the device
  * (current CUDA device) and copied to psf_out.  Bit-identical to OpenCV 4.x warpAffine. */
 int fdr_motion_psf_host(int length, double angle_deg, float* psf_out);
@@ -136,6 +177,8 @@ int fdr_motion_psf_host(int length, double angle_deg, float* psf_out);
 /* Counter-hash u8 images generated on the device, identical to oracle/orc_synth_u8. */
 int fdr_synth_images_device_u8(void* d_out_images, uint32_t seed, long long first_image, int n_images, int channels,
                                int rows, int cols, void* stream);
+/* Synchronous copy for harnesses holding raw device pointers: kind 0 = H2D, 1 = D2H, 2 = D2D. */
+int fdr_memcpy(void* dst, const void* src, size_t bytes, int kind);
 /* Overwrites `bytes` of scratch to evict L2 between timed iterations. */
 int fdr_l2_flush_device(void* d_scratch, size_t bytes, void* stream);
 

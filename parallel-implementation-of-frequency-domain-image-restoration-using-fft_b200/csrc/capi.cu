@@ -14,15 +14,12 @@
 #include <string>
 #include <vector>
 
-#include "../../include/fdr_b200.h"
-#include "passes.h"
+#include "capi_internal.h"
 
 using namespace fdr;
 
-namespace {
-
-thread_local std::string g_last_error;
-
+namespace fdr {
+static thread_local std::string g_last_error;
 int set_error(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -32,71 +29,15 @@ int set_error(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
+const char* last_error_text() { return g_last_error.c_str(); }
+}  // namespace fdr
 
-#define FDR_CUDA(call)                                                                                    \
-    do {                                                                                                  \
-        cudaError_t e__ = (call);                                                                         \
-        if (e__ != cudaSuccess)                                                                           \
-            return set_error(FDR_E_CUDA, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-    } while (0)
-
-#define FDR_TRY(call)            \
-    do {                         \
-        int rc__ = (call);       \
-        if (rc__ != FDR_OK) return rc__; \
-    } while (0)
-
-int next_pow2(int n) {  // utils.hpp:27-31
-    int p = 1;
-    while (p < n) p <<= 1;
-    return p;
-}
-bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+namespace {
 
 int ensure_device(int device) {
     FDR_CUDA(cudaSetDevice(device));
     return FDR_OK;
 }
-
-template <typename T> struct DevBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    int ensure(size_t count) {
-        if (count <= n) return FDR_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e != cudaSuccess) return set_error(FDR_E_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
-        n = count;
-        return FDR_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        n = 0;
-    }
-};
-
-template <typename T> struct PinBuf {
-    T* p = nullptr;
-    size_t n = 0;
-    int ensure(size_t count) {
-        if (count <= n) return FDR_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        n = 0;
-        cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
-        if (e != cudaSuccess) return set_error(FDR_E_NOMEM, "cudaMallocHost(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
-        n = count;
-        return FDR_OK;
-    }
-    void release() {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        n = 0;
-    }
-};
 
 bool is_pinned_or_device(const void* p) {
     cudaPointerAttributes at;
@@ -356,9 +297,27 @@ int build_wiener(fdr_plan* p) {
     return FDR_OK;
 }
 
+struct ScopedTimer {  // event pair on a stream, accumulating into a bucket (Profiler, fft_gpu.cu:17-57)
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    float* dst;
+    ScopedTimer(fdr_plan* p, int slot, cudaStream_t st, float* d) : a(p->ev[2 * slot]), b(p->ev[2 * slot + 1]), s(st), dst(d) {
+        cudaEventRecord(a, s);
+    }
+    void stop() {
+        cudaEventRecord(b, s);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        *dst += ms;
+    }
+};
+
+}  // namespace
+
 // Inverse rotation matrix exactly as OpenCV derives it (getRotationMatrix2D + warpAffine's
 // inversion, both in double); utils.hpp:16-22.
-PsfAffine motion_affine(int size, double angle_deg) {
+PsfAffine fdr::motion_affine(int size, double angle_deg) {
     const double CVPI = 3.1415926535897932384626433832795;
     const double cx = (double)(float)(size / 2), cy = (double)(float)(size / 2);
     double ang = angle_deg * (CVPI / 180);
@@ -383,27 +342,10 @@ PsfAffine motion_affine(int size, double angle_deg) {
     return a;
 }
 
-struct ScopedTimer {  // event pair on a stream, accumulating into a bucket (Profiler, fft_gpu.cu:17-57)
-    cudaEvent_t a, b;
-    cudaStream_t s;
-    float* dst;
-    ScopedTimer(fdr_plan* p, int slot, cudaStream_t st, float* d) : a(p->ev[2 * slot]), b(p->ev[2 * slot + 1]), s(st), dst(d) {
-        cudaEventRecord(a, s);
-    }
-    void stop() {
-        cudaEventRecord(b, s);
-        cudaEventSynchronize(b);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, a, b);
-        *dst += ms;
-    }
-};
-
-}  // namespace
 
 extern "C" {
 
-__attribute__((visibility("default"))) const char* fdr_last_error(void) { return g_last_error.c_str(); }
+__attribute__((visibility("default"))) const char* fdr_last_error(void) { return fdr::last_error_text(); }
 __attribute__((visibility("default"))) int fdr_version(void) { return 100; }
 
 __attribute__((visibility("default"))) int fdr_device_count(int* count) {
@@ -862,6 +804,14 @@ __attribute__((visibility("default"))) int fdr_dft_naive_host(float* data, int n
 
 __attribute__((visibility("default"))) int fdr_transform_rows_host(float* data, int rows, int n, int inverse) { return transform_host(data, rows, n, inverse, true, false); }
 
+// Plain copies for harnesses that hold raw device pointers (kind: 0 = H2D, 1 = D2H, 2 = D2D).
+__attribute__((visibility("default"))) int fdr_memcpy(void* dst, const void* src, size_t bytes, int kind) {
+    if (!dst || !src || kind < 0 || kind > 2) return set_error(FDR_E_INVALID, "bad arguments");
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    FDR_CUDA(cudaMemcpy(dst, src, bytes, k));
+    return FDR_OK;
+}
+
 __attribute__((visibility("default"))) int fdr_motion_psf_host(int length, double angle_deg, float* psf_out) {
     if (length < 1 || !psf_out) return set_error(FDR_E_INVALID, "bad PSF arguments");
     float* d = nullptr;
@@ -877,8 +827,8 @@ __attribute__((visibility("default"))) int fdr_synth_images_device_u8(void* d_ou
                                int cols, void* stream) {
     if (!d_out || n_images < 0 || channels < 1 || rows < 1 || cols < 1) return set_error(FDR_E_INVALID, "bad arguments");
     if (n_images == 0) return FDR_OK;
-    FDR_CUDA(launch_synth_u8(static_cast<uint8_t*>(d_out), seed, first_image, n_images, channels, rows, cols,
-                             static_cast<cudaStream_t>(stream)));
+    FDR_CUDA(launch_synth_u8(static_cast<uint8_t*>(d_out), seed, first_image, n_images, channels, (long long)rows * cols, 0,
+                             (long long)rows * cols, static_cast<cudaStream_t>(stream)));
     return FDR_OK;
 }
 

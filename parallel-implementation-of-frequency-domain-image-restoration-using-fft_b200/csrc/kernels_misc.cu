@@ -84,6 +84,28 @@ __global__ void minmax_finalize_kernel(const unsigned int* mm, float2* ss, float
         mmf[2 * i + 1] = (float)smax;
     }
 }
+__global__ void minmax_decode_kernel(const unsigned int* mm, float* mmf, int units) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * units) mmf[i] = f32_from_ordered(mm[i]);
+}
+cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, cudaStream_t s) {
+    minmax_decode_kernel<<<(2 * units + 127) / 128, 128, 0, s>>>(minmax, minmax_f32, units);
+    return cudaGetLastError();
+}
+
+__global__ void scale_shift_from_f32_kernel(const float* mmf, float2* ss, int units) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= units) return;
+    const double smin = (double)mmf[2 * i], smax = (double)mmf[2 * i + 1];
+    const double scale = (smax - smin) > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0;
+    const float a = (float)scale;
+    ss[i] = make_float2(a, 0.0f - (float)__dmul_rn(smin, (double)a));
+}
+cudaError_t launch_scale_shift_from_f32(const float* minmax_f32, float2* scale_shift, int units, cudaStream_t s) {
+    scale_shift_from_f32_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax_f32, scale_shift, units);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_minmax_finalize(const unsigned int* minmax, float2* scale_shift, float* minmax_f32, int units,
                                    cudaStream_t s) {
     minmax_finalize_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax, scale_shift, minmax_f32, units);
@@ -115,6 +137,31 @@ __global__ void pack_u8_kernel(const float* raw, long long ustride, const float2
     }
 }
 
+// C = 3, four pixels per thread: three 16-byte plane loads, three 4-byte stores (12 output bytes).
+__global__ void pack_u8_c3_vec4_kernel(const float* __restrict__ raw, long long ustride, const float2* __restrict__ ss,
+                                       uint8_t* __restrict__ out, long long nquads) {
+    const int img = blockIdx.y;
+    const float4* r0 = reinterpret_cast<const float4*>(raw + (long long)img * 3 * ustride);
+    const float4* r1 = reinterpret_cast<const float4*>(raw + ((long long)img * 3 + 1) * ustride);
+    const float4* r2 = reinterpret_cast<const float4*>(raw + ((long long)img * 3 + 2) * ustride);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + (long long)img * nquads * 12);
+    const float2 k0 = ss[img * 3], k1 = ss[img * 3 + 1], k2 = ss[img * 3 + 2];
+    auto q8 = [](float v, float2 k) -> uint32_t {
+        int q = __float2int_rn(fmaf(v, k.x, k.y) * 255.0f);
+        return (uint32_t)min(max(q, 0), 255);
+    };
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nquads; j += (long long)gridDim.x * blockDim.x) {
+        const float4 b = __ldg(r0 + j), g = __ldg(r1 + j), r = __ldg(r2 + j);
+        const uint32_t b0 = q8(b.x, k0), g0 = q8(g.x, k1), c0 = q8(r.x, k2);
+        const uint32_t b1 = q8(b.y, k0), g1 = q8(g.y, k1), c1 = q8(r.y, k2);
+        const uint32_t b2 = q8(b.z, k0), g2 = q8(g.z, k1), c2 = q8(r.z, k2);
+        const uint32_t b3 = q8(b.w, k0), g3 = q8(g.w, k1), c3 = q8(r.w, k2);
+        o[3 * j] = b0 | (g0 << 8) | (c0 << 16) | (b1 << 24);
+        o[3 * j + 1] = g1 | (c1 << 8) | (b2 << 16) | (g2 << 24);
+        o[3 * j + 2] = c2 | (b3 << 8) | (g3 << 16) | (c3 << 24);
+    }
+}
+
 __global__ void pack_u8_generic_kernel(const float* raw, long long ustride, const float2* ss, uint8_t* out, int C,
                                        int rows, int cols) {
     const int img = blockIdx.y;
@@ -134,7 +181,12 @@ cudaError_t launch_pack_u8(const float* raw, long long raw_unit_stride, const fl
     int bx = (int)((npx + 255) / 256);
     if (bx > 148 * 8) bx = 148 * 8;
     dim3 g(bx, imgs);
-    if (channels == 3)
+    if (channels == 3 && npx % 4 == 0 && raw_unit_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+        int bq = (int)((npx / 4 + 255) / 256);
+        if (bq > 148 * 8) bq = 148 * 8;
+        pack_u8_c3_vec4_kernel<<<dim3(bq, imgs), 256, 0, s>>>(raw, raw_unit_stride, scale_shift, out, npx / 4);
+    } else if (channels == 3)
         pack_u8_kernel<3><<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, out, rows, cols);
     else if (channels == 1)
         pack_u8_kernel<1><<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, out, rows, cols);
@@ -175,22 +227,24 @@ __device__ __forceinline__ uint32_t lowbias32(uint32_t v) {
     v ^= v >> 16;
     return v;
 }
-__global__ void synth_u8_kernel(uint8_t* out, uint32_t seed, long long img0, int C, long long npx) {
+__global__ void synth_u8_kernel(uint8_t* out, uint32_t seed, long long img0, int C, long long plane_px, long long px0,
+                                long long npx) {
     const int img = blockIdx.y;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x)
         for (int c = 0; c < C; ++c) {
-            const unsigned long long idx = ((unsigned long long)(img0 + img) * C + c) * (unsigned long long)npx + i;
+            const unsigned long long idx = ((unsigned long long)(img0 + img) * C + c) * (unsigned long long)plane_px + px0 + i;
             const uint32_t hi = lowbias32(seed + (uint32_t)(idx >> 32));
             out[((long long)img * npx + i) * C + c] = (uint8_t)(lowbias32((uint32_t)idx ^ hi) >> 24);
         }
 }
-cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, int rows, int cols,
-                            cudaStream_t s) {
-    const long long npx = (long long)rows * cols;
+// Pixels [px0, px0 + npx) of every plane (plane_px pixels each) of images img0 .. img0+imgs-1.
+cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, long long plane_px,
+                            long long px0, long long npx, cudaStream_t s) {
     int bx = (int)((npx + 255) / 256);
     if (bx > 148 * 8) bx = 148 * 8;
+    if (bx < 1) bx = 1;
     dim3 g(bx, imgs);
-    synth_u8_kernel<<<g, 256, 0, s>>>(out, seed, img0, channels, npx);
+    synth_u8_kernel<<<g, 256, 0, s>>>(out, seed, img0, channels, plane_px, px0, npx);
     return cudaGetLastError();
 }
 

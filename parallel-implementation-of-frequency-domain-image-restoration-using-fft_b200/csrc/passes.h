@@ -17,8 +17,12 @@
 
 namespace fdr {
 
-enum RowInMode { ROW_IN_PAIR_F32 = 0, ROW_IN_PAIR_U8 = 1, ROW_IN_COMPLEX = 2 };
-enum RowOutMode { ROW_OUT_COMPLEX = 0, ROW_OUT_REAL_PAIR = 1 };
+// ROW_IN_GATHER / ROW_OUT_SCATTER are the row-sharded (multi-GPU) forms: the row lives on this
+// GPU, its columns are spread over `world` column slabs [rows_padded][n/world], one per GPU, reached
+// through peer-mapped pointers (NVLink).  The transpose of the reference's MPI_Alltoallv
+// (/root/reference/fft/fft_mpi.cpp:170-279) is thereby fused into the row passes.
+enum RowInMode { ROW_IN_PAIR_F32 = 0, ROW_IN_PAIR_U8 = 1, ROW_IN_COMPLEX = 2, ROW_IN_GATHER = 3 };
+enum RowOutMode { ROW_OUT_COMPLEX = 0, ROW_OUT_REAL_PAIR = 1, ROW_OUT_SCATTER = 2 };
 enum ColMode { COL_FFT = 0, COL_WIENER = 1, COL_MAKE_WIENER = 2, COL_FILTER = 3 };
 
 struct RowPassArgs {
@@ -47,6 +51,11 @@ struct RowPassArgs {
     int raw_rows, raw_cols;      // H, W : only y < H, x < W is stored
     unsigned int* minmax;        // [local unit][2] ordered-uint encoded min, max over the PADDED plane
     int local_units;             // units in this chunk
+    // ---- row-sharded exchange (ROW_IN_GATHER / ROW_OUT_SCATTER) ----
+    float2* const* peers;        // device array [world]: base of every GPU's column slab (NULL = skip that peer)
+    int peer_shift;              // log2(n / world): column x belongs to peer x >> peer_shift
+    long long peer_plane;        // elements per pair in a slab = rows_padded * (n / world)
+    int row0;                    // global (padded) index of local row 0
 };
 
 struct ColPassArgs {
@@ -87,8 +96,10 @@ cudaError_t launch_pack_u8(const float* raw, long long raw_unit_stride, const fl
 // normalised f32 planes [unit][H][W]
 cudaError_t launch_normalize_f32(const float* raw, long long raw_unit_stride, const float2* scale_shift, float* out,
                                  long long out_unit_stride, int units, int rows, int cols, cudaStream_t s);
-cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, int rows, int cols,
-                            cudaStream_t s);
+cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, long long plane_px,
+                            long long px0, long long npx, cudaStream_t s);
+cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, cudaStream_t s);
+cudaError_t launch_scale_shift_from_f32(const float* minmax_f32, float2* scale_shift, int units, cudaStream_t s);
 // out-of-place batched O(n^2) DFT: element i of batch b at in[b*batch_stride + i*elem_stride]
 cudaError_t launch_dft_naive(const float2* in, float2* out, int n, long long elem_stride, int batch,
                              long long batch_stride, int inverse, cudaStream_t s);

@@ -51,6 +51,19 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
             if constexpr (CONJ) z.y = -z.y;
             v[m] = z;
         }
+    } else if constexpr (IN_MODE == ROW_IN_GATHER) {
+        const int cl_mask = (1 << a.peer_shift) - 1;
+        const long long off = (long long)pair * a.peer_plane + ((long long)(a.row0 + row) << a.peer_shift);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int x = t + T * m;
+            float2 z = make_float2(0.f, 0.f);
+            if (active) {
+                const float2* src = a.peers[x >> a.peer_shift];
+                z = src[off + (x & cl_mask)];
+            }
+            v[m] = z;
+        }
     } else if constexpr (IN_MODE == ROW_IN_PAIR_F32) {
         const float* p0 = a.in_f32 + (a.unit_base + u0) * a.in_unit_stride + (long long)row * a.in_row_stride;
         const float* p1 = has1 ? a.in_f32 + (a.unit_base + u1) * a.in_unit_stride + (long long)row * a.in_row_stride : p0;
@@ -88,7 +101,18 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
 
     fft_forward<N, 1>(v, ex, a.tw, t, 0);
 
-    if constexpr (OUT_MODE == ROW_OUT_COMPLEX) {
+    if constexpr (OUT_MODE == ROW_OUT_SCATTER) {
+        if (active) {
+            const int cl_mask = (1 << a.peer_shift) - 1;
+            const long long off = (long long)pair * a.peer_plane + ((long long)(a.row0 + row) << a.peer_shift);
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int x = t + T * m;
+                float2* dst = a.peers[x >> a.peer_shift];
+                if (dst) dst[off + (x & cl_mask)] = v[m];
+            }
+        }
+    } else if constexpr (OUT_MODE == ROW_OUT_COMPLEX) {
         if (active) {
             float2* dst = a.cout + (long long)pair * a.cplane + (long long)row * N + t;
 #pragma unroll
@@ -268,6 +292,9 @@ template <int LOGN> cudaError_t launch_row_pass_t(const RowPassArgs& a, cudaStre
     if (a.in_mode == ROW_IN_PAIR_U8 && a.out_mode == ROW_OUT_COMPLEX) return launch_row_variant<LOGN, ROW_IN_PAIR_U8, ROW_OUT_COMPLEX, false>(a, s);
     if (a.in_mode == ROW_IN_PAIR_F32 && a.out_mode == ROW_OUT_COMPLEX) return launch_row_variant<LOGN, ROW_IN_PAIR_F32, ROW_OUT_COMPLEX, false>(a, s);
     if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_REAL_PAIR) return launch_row_variant<LOGN, ROW_IN_COMPLEX, ROW_OUT_REAL_PAIR, false>(a, s);
+    if (a.in_mode == ROW_IN_PAIR_U8 && a.out_mode == ROW_OUT_SCATTER) return launch_row_variant<LOGN, ROW_IN_PAIR_U8, ROW_OUT_SCATTER, false>(a, s);
+    if (a.in_mode == ROW_IN_PAIR_F32 && a.out_mode == ROW_OUT_SCATTER) return launch_row_variant<LOGN, ROW_IN_PAIR_F32, ROW_OUT_SCATTER, false>(a, s);
+    if (a.in_mode == ROW_IN_GATHER && a.out_mode == ROW_OUT_REAL_PAIR) return launch_row_variant<LOGN, ROW_IN_GATHER, ROW_OUT_REAL_PAIR, false>(a, s);
     if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_COMPLEX && !a.conj)
         return launch_row_variant<LOGN, ROW_IN_COMPLEX, ROW_OUT_COMPLEX, false>(a, s);
     if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_COMPLEX && a.conj)

@@ -1,0 +1,370 @@
+// shard.cu -- one rank's share of a ROW-SHARDED restoration of a single large image over
+// `world` GPUs (BASELINE configs[4]: 16384 x 16384 over 2/4/8 B200).
+//
+// Decomposition (the reference's MPI mode is the behavioural model,
+// /root/reference/fft/fft_mpi.cpp:89-100 row slabs, :170-279 all-to-all transpose, :311-470):
+//   rank g owns padded rows [g*Rp/G, (g+1)*Rp/G) in the row passes and padded columns
+//   [g*Cp/G, (g+1)*Cp/G) in the column pass.  Every rank allocates one column slab
+//   [pairs][Rp][Cp/G] (complex).
+//     phase 1  local rows: load u8, FFT along x, and STORE each element straight into the column
+//              slab of the GPU that owns its column (peer-mapped pointer, NVLink) -- the
+//              all-to-all transpose is the epilogue of the row pass, not a separate collective;
+//     barrier  (caller: any stream-ordered cross-rank barrier, e.g. an NCCL all-reduce)
+//     phase 2  local column slab: FFT along y, Wiener factor, inverse FFT along y, in place;
+//     barrier
+//     phase 3  local rows again: LOAD every element from the owning GPU's slab (peer reads),
+//              inverse FFT along x, split the two packed planes, local min/max;
+//     all-reduce(min), all-reduce(max) of 2 floats per plane (caller; doubles as the barrier
+//              that protects the slabs before the next image)
+//     phase 4  normalise + pack the local rows.
+//   2 exchanges per plane pair instead of the reference's 6 MPI_Alltoallv per channel
+//   (fft_mpi.cpp:386,393,423).  No scatter/gather to a root: every rank reads and writes only
+//   its own rows of the image.
+// Several shards may live in one process on one device (peers = plain device pointers): that is
+// how the single-GPU test suite exercises this code.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "capi_internal.h"
+
+using namespace fdr;
+
+struct fdr_shard {
+    int device = 0, rank = 0, world = 1;
+    int H = 0, W = 0, C = 0, Rp = 0, Cp = 0;
+    int Rl = 0, Cl = 0;          // padded rows / columns per rank
+    int row0 = 0, rows_local = 0;  // image rows [row0, row0 + rows_local) live here
+    int npairs = 0;
+    float K = 0.f;
+    bool have_wiener = false, have_peers = false;
+    cudaStream_t stream = nullptr;
+    DevBuf<float2> slab;      // [npairs][Rp][Cl]
+    DevBuf<float2> wiener;    // [Rp][Cl]
+    DevBuf<float> raw;        // [C][rows_local][W]
+    DevBuf<unsigned int> mm;  // [C][2] ordered
+    DevBuf<float> mmf;        // [C][2] floats: min, max (all-reduced by the caller)
+    DevBuf<float2> ss;        // [C] scale, shift
+    DevBuf<float> psf;
+    DevBuf<float2*> peers;    // [world] device copy of the peer slab table
+    DevBuf<float2*> self_only;  // [world] table with only this rank's slab (Wiener build)
+    int psf_rows = 0, psf_cols = 0;
+    const float2* tw_rows = nullptr;
+    const float2* tw_cols = nullptr;
+    long long launches = 0;
+};
+
+namespace {
+cudaStream_t pick(fdr_shard* s, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : s->stream; }
+
+int build_wiener(fdr_shard* s) {
+    if (s->psf_rows > s->Rp || s->psf_cols > s->Cp)
+        return set_error(FDR_E_INVALID, "PSF %dx%d larger than the padded image %dx%d", s->psf_rows, s->psf_cols, s->Rp, s->Cp);
+    cudaStream_t st = s->stream;
+    // PSF rows are few (S <= Rp): every rank transforms all of them and keeps its own columns.
+    RowPassArgs r{};
+    r.n = s->Cp;
+    r.nrows = s->psf_rows;
+    r.npairs = 1;
+    r.in_mode = ROW_IN_PAIR_F32;
+    r.out_mode = ROW_OUT_SCATTER;
+    r.in_f32 = s->psf.p;
+    r.in_unit_stride = (long long)s->psf_rows * s->psf_cols;
+    r.in_row_stride = s->psf_cols;
+    r.channels = 1;
+    r.img_rows = s->psf_rows;
+    r.img_cols = s->psf_cols;
+    r.units_total = 1;
+    r.tw = s->tw_rows;
+    r.peers = s->self_only.p;
+    r.peer_shift = ilog2(s->Cl);
+    r.peer_plane = (long long)s->Rp * s->Cl;
+    r.row0 = 0;
+    FDR_CUDA(launch_row_pass(r, st));
+    ColPassArgs c{};
+    c.n = s->Rp;
+    c.pitch = s->Cl;
+    c.npairs = 1;
+    c.mode = COL_MAKE_WIENER;
+    c.rows_valid = s->psf_rows;
+    c.data = s->slab.p;
+    c.cplane = (long long)s->Rp * s->Cl;
+    c.wiener_out = s->wiener.p;
+    c.K = s->K;
+    c.tw = s->tw_cols;
+    FDR_CUDA(launch_col_pass(c, st));
+    FDR_CUDA(cudaStreamSynchronize(st));
+    s->have_wiener = true;
+    return FDR_OK;
+}
+}  // namespace
+
+FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, int rank, int world, int device) {
+    if (!out) return set_error(FDR_E_INVALID, "shard is NULL");
+    *out = nullptr;
+    if (rows < 1 || cols < 1 || channels < 1) return set_error(FDR_E_INVALID, "bad image geometry %dx%dx%d", rows, cols, channels);
+    if (world < 1 || !is_pow2(world) || rank < 0 || rank >= world)
+        return set_error(FDR_E_INVALID, "world=%d must be a power of two and 0 <= rank=%d < world", world, rank);
+    const int Rp = next_pow2(rows), Cp = next_pow2(cols);
+    if (Rp > 16384 || Cp > 16384) return set_error(FDR_E_INVALID, "padded size above 16384 is not supported");
+    if (Rp / world < 1 || Cp / world < 1) return set_error(FDR_E_INVALID, "image %dx%d too small to split over %d ranks", Rp, Cp, world);
+    FDR_CUDA(cudaSetDevice(device));
+    fdr_shard* s = new (std::nothrow) fdr_shard();
+    if (!s) return set_error(FDR_E_NOMEM, "out of host memory");
+    s->device = device;
+    s->rank = rank;
+    s->world = world;
+    s->H = rows;
+    s->W = cols;
+    s->C = channels;
+    s->Rp = Rp;
+    s->Cp = Cp;
+    s->Rl = Rp / world;
+    s->Cl = Cp / world;
+    s->row0 = rank * s->Rl;
+    int r1 = s->row0 + s->Rl;
+    if (r1 > rows) r1 = rows;
+    s->rows_local = r1 > s->row0 ? r1 - s->row0 : 0;
+    s->npairs = (channels + 1) / 2;
+    int rc = FDR_OK;
+    cudaError_t e = get_twiddles(Cp, &s->tw_rows);
+    if (e == cudaSuccess) e = get_twiddles(Rp, &s->tw_cols);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "shard setup: %s", cudaGetErrorString(e));
+    if (rc == FDR_OK) rc = s->slab.ensure((size_t)s->npairs * Rp * s->Cl);
+    if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Cl);
+    if (rc == FDR_OK) rc = s->raw.ensure((size_t)channels * (s->rows_local > 0 ? s->rows_local : 1) * cols);
+    if (rc == FDR_OK) rc = s->mm.ensure((size_t)channels * 2);
+    if (rc == FDR_OK) rc = s->mmf.ensure((size_t)channels * 2);
+    if (rc == FDR_OK) rc = s->ss.ensure((size_t)channels);
+    if (rc == FDR_OK) rc = s->peers.ensure((size_t)world);
+    if (rc == FDR_OK) rc = s->self_only.ensure((size_t)world);
+    if (rc == FDR_OK) {
+        std::vector<float2*> tbl((size_t)world, nullptr);
+        tbl[(size_t)rank] = s->slab.p;
+        e = cudaMemcpy(s->self_only.p, tbl.data(), sizeof(float2*) * world, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "peer table: %s", cudaGetErrorString(e));
+    }
+    if (rc != FDR_OK) {
+        fdr_shard_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_destroy(fdr_shard* s) {
+    if (!s) return FDR_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    s->slab.release();
+    s->wiener.release();
+    s->raw.release();
+    s->mm.release();
+    s->mmf.release();
+    s->ss.release();
+    s->psf.release();
+    s->peers.release();
+    s->self_only.release();
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_geometry(const fdr_shard* s, int* first_row, int* n_rows, int* padded_rows, int* padded_cols,
+                               int* cols_per_rank) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    if (first_row) *first_row = s->row0;
+    if (n_rows) *n_rows = s->rows_local;
+    if (padded_rows) *padded_rows = s->Rp;
+    if (padded_cols) *padded_cols = s->Cp;
+    if (cols_per_rank) *cols_per_rank = s->Cl;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_local_slab(const fdr_shard* s, void** d_slab, size_t* bytes) {
+    if (!s || !d_slab) return set_error(FDR_E_INVALID, "bad arguments");
+    *d_slab = s->slab.p;
+    if (bytes) *bytes = s->slab.n * sizeof(float2);
+    return FDR_OK;
+}
+
+FDR_API int fdr_ipc_export(const void* dptr, unsigned char handle[64]) {
+    if (!dptr || !handle) return set_error(FDR_E_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    FDR_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+    memcpy(handle, &h, 64);
+    return FDR_OK;
+}
+
+FDR_API int fdr_ipc_open(const unsigned char handle[64], void** dptr) {
+    if (!dptr || !handle) return set_error(FDR_E_INVALID, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    FDR_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FDR_OK;
+}
+
+FDR_API int fdr_ipc_close(void* dptr) {
+    if (dptr) FDR_CUDA(cudaIpcCloseMemHandle(dptr));
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_set_peers(fdr_shard* s, void* const* slabs) {
+    if (!s || !slabs) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_CUDA(cudaSetDevice(s->device));
+    std::vector<float2*> tbl((size_t)s->world);
+    for (int i = 0; i < s->world; ++i) {
+        tbl[(size_t)i] = (i == s->rank) ? s->slab.p : static_cast<float2*>(slabs[i]);
+        if (!tbl[(size_t)i]) return set_error(FDR_E_INVALID, "peer %d slab is NULL", i);
+    }
+    FDR_CUDA(cudaMemcpy(s->peers.p, tbl.data(), sizeof(float2*) * s->world, cudaMemcpyHostToDevice));
+    s->have_peers = true;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_set_psf_motion(fdr_shard* s, int length, double angle_deg, float K) {
+    if (!s || length < 1) return set_error(FDR_E_INVALID, "bad PSF arguments");
+    FDR_CUDA(cudaSetDevice(s->device));
+    FDR_TRY(s->psf.ensure((size_t)length * length));
+    FDR_CUDA(launch_motion_psf(s->psf.p, length, motion_affine(length, angle_deg), s->stream));
+    s->psf_rows = s->psf_cols = length;
+    s->K = K;
+    return build_wiener(s);
+}
+
+FDR_API int fdr_shard_set_psf_host(fdr_shard* s, const float* psf, int psf_rows, int psf_cols, float K) {
+    if (!s || !psf || psf_rows < 1 || psf_cols < 1) return set_error(FDR_E_INVALID, "bad PSF arguments");
+    FDR_CUDA(cudaSetDevice(s->device));
+    FDR_TRY(s->psf.ensure((size_t)psf_rows * psf_cols));
+    FDR_CUDA(cudaMemcpy(s->psf.p, psf, sizeof(float) * (size_t)psf_rows * psf_cols, cudaMemcpyHostToDevice));
+    s->psf_rows = psf_rows;
+    s->psf_cols = psf_cols;
+    s->K = K;
+    return build_wiener(s);
+}
+
+// phase 1: rows forward + scatter to the owners of the columns.  d_in_rows: this rank's rows of
+// the image, interleaved u8 [rows_local][W][C].
+FDR_API int fdr_shard_phase1_rows(fdr_shard* s, const void* d_in_rows_u8, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    if (!s->have_peers || !s->have_wiener) return set_error(FDR_E_STATE, "set peers and PSF before phase 1");
+    FDR_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = pick(s, stream);
+    s->launches = 0;
+    FDR_CUDA(launch_minmax_reset(s->mm.p, s->C, st));
+    s->launches += 1;
+    if (s->rows_local == 0) return FDR_OK;  // slab entirely inside the zero padding
+    if (!d_in_rows_u8) return set_error(FDR_E_INVALID, "input rows are NULL");
+    RowPassArgs r{};
+    r.n = s->Cp;
+    r.nrows = s->rows_local;
+    r.npairs = s->npairs;
+    r.in_mode = ROW_IN_PAIR_U8;
+    r.out_mode = ROW_OUT_SCATTER;
+    r.in_u8 = static_cast<const uint8_t*>(d_in_rows_u8);
+    r.channels = s->C;
+    r.img_rows = s->rows_local;
+    r.img_cols = s->W;
+    r.unit_base = 0;
+    r.units_total = s->C;
+    r.tw = s->tw_rows;
+    r.peers = s->peers.p;
+    r.peer_shift = ilog2(s->Cl);
+    r.peer_plane = (long long)s->Rp * s->Cl;
+    r.row0 = s->row0;
+    FDR_CUDA(launch_row_pass(r, st));
+    s->launches += 1;
+    return FDR_OK;
+}
+
+// phase 2: columns of the local slab, in place (FFT, Wiener factor, inverse FFT).
+FDR_API int fdr_shard_phase2_cols(fdr_shard* s, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    FDR_CUDA(cudaSetDevice(s->device));
+    ColPassArgs c{};
+    c.n = s->Rp;
+    c.pitch = s->Cl;
+    c.npairs = s->npairs;
+    c.mode = COL_WIENER;
+    c.rows_valid = s->H;
+    c.data = s->slab.p;
+    c.cplane = (long long)s->Rp * s->Cl;
+    c.wiener = s->wiener.p;
+    c.K = s->K;
+    c.tw = s->tw_cols;
+    FDR_CUDA(launch_col_pass(c, pick(s, stream)));
+    s->launches += 1;
+    return FDR_OK;
+}
+
+// phase 3: gather the local padded rows from every slab, inverse rows, min/max of the local part.
+FDR_API int fdr_shard_phase3_rows(fdr_shard* s, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    FDR_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = pick(s, stream);
+    RowPassArgs r{};
+    r.n = s->Cp;
+    r.nrows = s->Rl;
+    r.npairs = s->npairs;
+    r.in_mode = ROW_IN_GATHER;
+    r.out_mode = ROW_OUT_REAL_PAIR;
+    r.unit_base = 0;
+    r.units_total = s->C;
+    r.raw = s->raw.p;
+    r.raw_unit_stride = (long long)(s->rows_local > 0 ? s->rows_local : 1) * s->W;
+    r.raw_rows = s->rows_local;
+    r.raw_cols = s->W;
+    r.minmax = s->mm.p;
+    r.local_units = s->C;
+    r.tw = s->tw_rows;
+    r.peers = s->peers.p;
+    r.peer_shift = ilog2(s->Cl);
+    r.peer_plane = (long long)s->Rp * s->Cl;
+    r.row0 = s->row0;
+    FDR_CUDA(launch_row_pass(r, st));
+    FDR_CUDA(launch_minmax_decode(s->mm.p, s->mmf.p, s->C, st));
+    s->launches += 2;
+    return FDR_OK;
+}
+
+// [channels][2] floats on the device (min, max of the local rows of every padded plane).  The
+// caller all-reduces column 0 with MIN and column 1 with MAX across ranks, in place.
+FDR_API int fdr_shard_minmax_device(fdr_shard* s, void** d_minmax_f32) {
+    if (!s || !d_minmax_f32) return set_error(FDR_E_INVALID, "bad arguments");
+    *d_minmax_f32 = s->mmf.p;
+    return FDR_OK;
+}
+
+// phase 4: normalise with the global extrema and pack this rank's rows: u8 [rows_local][W][C].
+FDR_API int fdr_shard_phase4_pack(fdr_shard* s, void* d_out_rows_u8, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    FDR_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = pick(s, stream);
+    FDR_CUDA(launch_scale_shift_from_f32(s->mmf.p, s->ss.p, s->C, st));
+    s->launches += 1;
+    if (s->rows_local == 0) return FDR_OK;
+    if (!d_out_rows_u8) return set_error(FDR_E_INVALID, "output rows are NULL");
+    FDR_CUDA(launch_pack_u8(s->raw.p, (long long)s->rows_local * s->W, s->ss.p, static_cast<uint8_t*>(d_out_rows_u8), 1, s->C,
+                            s->rows_local, s->W, st));
+    s->launches += 1;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_last_launch_count(const fdr_shard* s, long long* launches) {
+    if (!s || !launches) return set_error(FDR_E_INVALID, "bad arguments");
+    *launches = s->launches;
+    return FDR_OK;
+}
+
+// Rows [first_row, first_row + n_rows) of synthetic image `image` (counter hash of the whole image).
+FDR_API int fdr_synth_rows_device_u8(void* d_out, uint32_t seed, long long image, int channels, int rows_total, int cols,
+                                     int first_row, int n_rows, void* stream) {
+    if (!d_out || channels < 1 || rows_total < 1 || cols < 1 || first_row < 0 || n_rows < 0 || first_row + n_rows > rows_total)
+        return set_error(FDR_E_INVALID, "bad arguments");
+    if (n_rows == 0) return FDR_OK;
+    FDR_CUDA(launch_synth_u8(static_cast<uint8_t*>(d_out), seed, image, 1, channels, (long long)rows_total * cols,
+                             (long long)first_row * cols, (long long)n_rows * cols, static_cast<cudaStream_t>(stream)));
+    return FDR_OK;
+}

@@ -72,6 +72,24 @@ def lib():
             "fdr_dft_naive_host": [_fp, i, i],
             "fdr_transform_rows_host": [_fp, i, i, i],
             "fdr_motion_psf_host": [i, d, _fp],
+            "fdr_memcpy": [vp, vp, sz, i],
+            "fdr_shard_create": [pp, i, i, i, i, i, i],
+            "fdr_shard_destroy": [vp],
+            "fdr_shard_geometry": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)],
+            "fdr_shard_local_slab": [vp, pp, C.POINTER(sz)],
+            "fdr_ipc_export": [vp, C.c_char_p],
+            "fdr_ipc_open": [C.c_char_p, pp],
+            "fdr_ipc_close": [vp],
+            "fdr_shard_set_peers": [vp, pp],
+            "fdr_shard_set_psf_motion": [vp, i, d, f],
+            "fdr_shard_set_psf_host": [vp, _fp, i, i, f],
+            "fdr_shard_phase1_rows": [vp, vp, vp],
+            "fdr_shard_phase2_cols": [vp, vp],
+            "fdr_shard_phase3_rows": [vp, vp],
+            "fdr_shard_minmax_device": [vp, pp],
+            "fdr_shard_phase4_pack": [vp, vp, vp],
+            "fdr_shard_last_launch_count": [vp, C.POINTER(ll)],
+            "fdr_synth_rows_device_u8": [vp, C.c_uint32, ll, i, i, i, i, i, vp],
             "fdr_synth_images_device_u8": [vp, C.c_uint32, ll, i, i, i, i, vp],
             "fdr_l2_flush_device": [vp, sz, vp],
         }
@@ -235,6 +253,91 @@ class Plan:
         out = np.empty(self.padded, np.complex64)
         _check(lib().fdr_plan_filtered_spectrum_host(self.h, _p(plane), 0, _p(out.view(np.float32))))
         return out
+
+
+class Shard:
+    """One rank's share of a row-sharded restoration (include/fdr_b200.h, fdr_shard_*)."""
+
+    def __init__(self, rows, cols, channels, rank, world, device=0):
+        self.h = C.c_void_p()
+        self.rows, self.cols, self.channels, self.rank, self.world = rows, cols, channels, rank, world
+        _check(lib().fdr_shard_create(C.byref(self.h), rows, cols, channels, rank, world, device))
+        v = [C.c_int() for _ in range(5)]
+        _check(lib().fdr_shard_geometry(self.h, *[C.byref(x) for x in v]))
+        self.first_row, self.n_rows, self.padded_rows, self.padded_cols, self.cols_per_rank = [x.value for x in v]
+        self._opened = []
+
+    def close(self):
+        if self.h:
+            for ptr in self._opened:
+                lib().fdr_ipc_close(ptr)
+            self._opened = []
+            lib().fdr_shard_destroy(self.h)
+            self.h = None
+
+    def local_slab(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        _check(lib().fdr_shard_local_slab(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def export_handle(self):
+        buf = C.create_string_buffer(64)
+        _check(lib().fdr_ipc_export(self.local_slab()[0], buf))
+        return buf.raw
+
+    def set_peers_from_handles(self, handles):
+        ptrs = []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                ptrs.append(self.local_slab()[0])
+            else:
+                ptr = C.c_void_p()
+                _check(lib().fdr_ipc_open(hb, C.byref(ptr)))
+                self._opened.append(ptr)
+                ptrs.append(ptr.value)
+        self.set_peers(ptrs)
+
+    def set_peers(self, ptrs):
+        arr = (C.c_void_p * self.world)(*ptrs)
+        _check(lib().fdr_shard_set_peers(self.h, arr))
+
+    def set_psf_motion(self, length, angle, K=0.01):
+        _check(lib().fdr_shard_set_psf_motion(self.h, int(length), float(angle), K))
+
+    def set_psf(self, psf, K=0.01):
+        psf = _f32(psf)
+        _check(lib().fdr_shard_set_psf_host(self.h, _p(psf), psf.shape[0], psf.shape[1], K))
+
+    def phase1(self, d_in_rows, stream=0):
+        _check(lib().fdr_shard_phase1_rows(self.h, d_in_rows, stream))
+
+    def phase2(self, stream=0):
+        _check(lib().fdr_shard_phase2_cols(self.h, stream))
+
+    def phase3(self, stream=0):
+        _check(lib().fdr_shard_phase3_rows(self.h, stream))
+
+    def minmax_ptr(self):
+        ptr = C.c_void_p()
+        _check(lib().fdr_shard_minmax_device(self.h, C.byref(ptr)))
+        return ptr.value
+
+    def phase4(self, d_out_rows, stream=0):
+        _check(lib().fdr_shard_phase4_pack(self.h, d_out_rows, stream))
+
+    def last_launch_count(self):
+        n = C.c_longlong(0)
+        _check(lib().fdr_shard_last_launch_count(self.h, C.byref(n)))
+        return n.value
+
+
+def memcpy(dst, src, nbytes, kind):
+    """kind: 0 = H2D, 1 = D2H, 2 = D2D (raw pointers / numpy .ctypes.data)."""
+    _check(lib().fdr_memcpy(dst, src, nbytes, kind))
+
+
+def synth_rows_device_u8(d_out, seed, image, channels, rows_total, cols, first_row, n_rows, stream=0):
+    _check(lib().fdr_synth_rows_device_u8(d_out, seed, image, channels, rows_total, cols, first_row, n_rows, stream))
 
 
 def dft2d(m, inverse=False):

@@ -1,0 +1,98 @@
+"""Partitioner for one 8 x B200 box (torch.distributed plumbing over NCCL/NVLink; every kernel is
+in lib/libfdr_b200.so).
+
+Two granularities:
+  * batches / colour planes -- independent: images_for_rank() gives each rank a contiguous block
+    of images; no data-path collective (bench.py --gpus N).
+  * one very large image -- ShardedRestorer: row slabs per rank, the transposes fused into the row
+    passes as peer stores/loads, cross-rank barriers and the 2-float min/max all-reduce through
+    torch.distributed.  Replaces the reference's MPI driver loop (mpi.cpp:95-111 +
+    fft_mpi.cpp:311-470).
+"""
+import torch
+import torch.distributed as dist
+
+
+def next_pow2(n):
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+def row_slab(rank, world, image_rows):
+    """Image rows [first, first+n) owned by `rank`: the padded rows are split evenly
+    (fft_mpi.cpp:89-100 calculate_distribution on a power of two has no remainder) and the part
+    beyond the image is zero padding nobody stores.  Must equal fdr_shard_geometry()."""
+    rl = next_pow2(image_rows) // world
+    first = rank * rl
+    last = min(first + rl, image_rows)
+    return first, max(0, last - first)
+
+
+def images_for_rank(rank, world, n_images):
+    """Contiguous block of images for `rank` (first `n_images % world` ranks get one more)."""
+    base, rem = divmod(n_images, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+class _DevView:
+    """__cuda_array_interface__ view over raw device memory, for torch.as_tensor (zero copy)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, shape, device, typestr="<f4"):
+    return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)
+
+
+class ShardedRestorer:
+    """Per-rank driver of the row-sharded restoration.  `backend` is an fdr.Shard (CUDA) or any
+    object with the same phase API (the CPU gloo test passes a numpy stand-in)."""
+
+    def __init__(self, backend, group=None, device=None):
+        self.b = backend
+        self.group = group
+        self.device = device
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        assert self.rank == backend.rank and self.world == backend.world
+        # exchange the slab handles (64-byte CUDA IPC handles, or whatever the backend exports)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, backend.export_handle(), group=group)
+        else:
+            handles[0] = backend.export_handle()
+        backend.set_peers_from_handles(handles)
+        self._mm = backend.minmax_tensor(device)      # [channels][2] view, all-reduced in place
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self._mm.device)
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier: a 1-element all-reduce on the current stream."""
+        if self.world > 1:
+            dist.all_reduce(self._flag, group=self.group)
+
+    def restore_rows(self, d_in_rows, d_out_rows, stream=0):
+        b = self.b
+        b.phase1(d_in_rows, stream)
+        self.barrier()                      # every slab has received all its columns
+        b.phase2(stream)
+        self.barrier()                      # every slab holds the filtered, column-inverted data
+        b.phase3(stream)
+        if self.world > 1:                  # global extrema of every padded plane (also the barrier
+            mn = self._mm[:, 0].contiguous()  # that frees the slabs for the next image)
+            mx = self._mm[:, 1].contiguous()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            self._mm[:, 0].copy_(mn)
+            self._mm[:, 1].copy_(mx)
+        b.phase4(d_out_rows, stream)
+
+
+def cuda_shard_backend(fdr, rows, cols, channels, rank, world, device_index):
+    """fdr.Shard plus the two hooks ShardedRestorer needs."""
+    sh = fdr.Shard(rows, cols, channels, rank, world, device_index)
+    sh.minmax_tensor = lambda device: device_tensor(sh.minmax_ptr(), (channels, 2), device or torch.device("cuda", device_index))
+    return sh
