@@ -68,6 +68,8 @@ struct fdr_plan {
     DevBuf<float> mmf;            // chunk units x 2
     DevBuf<float2> wiener;        // Rp x Cp
     DevBuf<float> psf;            // psf_rows x psf_cols
+    int persistent_sms = 0;           // SM count when the persistent column kernel is enabled
+    int tiled = 0;                    // column-tiled spectrum/Wiener layout inside the restore pipeline (FDR_TILED=1)
     const float2* tw_rows = nullptr;  // twiddles for length Cp (row passes)
     const float2* tw_cols = nullptr;  // twiddles for length Rp (column passes)
     // staging for the host entry points
@@ -194,6 +196,9 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r1.cout = p->spec.p;
         r1.cplane = (long long)p->plane_elems();
         r1.tw = p->tw_rows;
+        r1.tiled = p->tiled;
+        r1.tile_shift = ilog2(col_pass_tile_width(p->Rp));
+        r1.tile_rows_shift = ilog2(p->Rp);
         const double px_in = (double)p->H * p->W * (in.mode == ROW_IN_PAIR_U8 ? 1.0 : 4.0) * nu;
         const double P = (double)p->plane_elems();
         {
@@ -212,6 +217,9 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         c2.wiener = p->wiener.p;
         c2.K = p->K;
         c2.tw = p->tw_cols;
+        c2.persistent_sms = p->persistent_sms;
+        c2.data_tiled = p->tiled;
+        c2.wiener_tiled = p->tiled;
         {
             KernelTimer kt(p, s, 1, (8.0 * p->H * p->Cp + 16.0 * P) * np);
             FDR_CUDA(launch_col_pass(c2, s));
@@ -234,6 +242,9 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r3.minmax = p->mm.p;
         r3.local_units = nu;
         r3.tw = p->tw_rows;
+        r3.tiled = p->tiled;
+        r3.tile_shift = ilog2(col_pass_tile_width(p->Rp));
+        r3.tile_rows_shift = ilog2(p->Rp);
         {
             KernelTimer kt(p, s, 2, 8.0 * P * np + 4.0 * HW * nu);
             FDR_CUDA(launch_row_pass(r3, s));
@@ -291,6 +302,7 @@ int build_wiener(fdr_plan* p) {
     c.wiener_out = p->wiener.p;
     c.K = p->K;
     c.tw = p->tw_cols;
+    c.wiener_tiled = p->tiled;
     FDR_CUDA(launch_col_pass(c, s));
     FDR_CUDA(cudaStreamSynchronize(s));
     p->have_wiener = true;
@@ -386,6 +398,17 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
     p->max_images = max_images;
     p->Rp = next_pow2(rows);
     p->Cp = next_pow2(cols);
+    {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const char* env = getenv("FDR_COL_PERSISTENT");
+        p->persistent_sms = (env && atoi(env) != 0) ? sms : 0;  // opt-in: measured slower than 2 CTAs/SM
+        const char* tl = getenv("FDR_TILED");
+        if (tl) p->tiled = atoi(tl) != 0;
+        if (p->Cp % col_pass_tile_width(p->Rp) != 0) p->tiled = 0;  // narrow images: plain row-major
+        const char* fg = getenv("FDR_L2_FETCH");
+        if (fg && atoi(fg) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
+    }
     cudaError_t e = get_twiddles(p->Cp, &p->tw_rows);
     if (e == cudaSuccess) e = get_twiddles(p->Rp, &p->tw_cols);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
@@ -485,7 +508,18 @@ __attribute__((visibility("default"))) int fdr_plan_get_wiener_host(const fdr_pl
     if (!p || !wf) return set_error(FDR_E_INVALID, "bad arguments");
     if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
     FDR_CUDA(cudaSetDevice(p->device));
-    FDR_CUDA(cudaMemcpy(wf, p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
+    if (!p->tiled) {
+        FDR_CUDA(cudaMemcpy(wf, p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
+        return FDR_OK;
+    }
+    // stored column-tiled [col/CW][row][col%CW]; hand back row-major (layout conversion only)
+    std::vector<float2> tmp(p->plane_elems());
+    FDR_CUDA(cudaMemcpy(tmp.data(), p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
+    const int cw = col_pass_tile_width(p->Rp);
+    float2* out = reinterpret_cast<float2*>(wf);
+    for (int g = 0; g < (p->Cp + cw - 1) / cw; ++g)
+        for (int r = 0; r < p->Rp; ++r)
+            for (int c = 0; c < cw && g * cw + c < p->Cp; ++c) out[(size_t)r * p->Cp + (size_t)g * cw + c] = tmp[((size_t)g * p->Rp + r) * cw + c];
     return FDR_OK;
 }
 
@@ -655,6 +689,54 @@ __attribute__((visibility("default"))) int fdr_plan_get_kernel_timing(fdr_plan* 
     return FDR_OK;
 }
 
+// Timing probe: runs one pass `reps` times on a workspace of `npairs` plane pairs and returns the
+// mean device time.  pass: 1 = rows forward (u8 in), 2 = columns, 3 = rows inverse + min/max.
+// variant (pass 2): 0 = Wiener, default dispatch; 1 = Wiener, non-persistent kernel; 2 = one forward FFT;
+// 3 = load + store only.
+__attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int pass, int variant, int npairs, int reps, float* ms_avg) {
+    if (!p || !ms_avg || npairs < 1 || reps < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
+    FDR_TRY(ensure_device(p->device));
+    const int nu = 2 * npairs;
+    FDR_TRY(ensure_workspace(p, nu));
+    FDR_TRY(p->d_in_u8.ensure((size_t)nu * p->H * p->W));
+    cudaStream_t s = p->stream;
+    FDR_CUDA(launch_synth_u8(p->d_in_u8.p, 12345u, 0, 1, nu, (long long)p->H * p->W, 0, (long long)p->H * p->W, s));
+    RowPassArgs r1{};
+    r1.n = p->Cp; r1.nrows = p->H; r1.npairs = npairs; r1.in_mode = ROW_IN_PAIR_U8; r1.out_mode = ROW_OUT_COMPLEX;
+    r1.in_u8 = p->d_in_u8.p; r1.channels = nu; r1.img_rows = p->H; r1.img_cols = p->W; r1.units_total = nu;
+    r1.cout = p->spec.p; r1.cplane = (long long)p->plane_elems(); r1.tw = p->tw_rows;
+    r1.tiled = p->tiled; r1.tile_shift = ilog2(col_pass_tile_width(p->Rp)); r1.tile_rows_shift = ilog2(p->Rp);
+    ColPassArgs c2{};
+    c2.n = p->Rp; c2.pitch = p->Cp; c2.npairs = npairs; c2.rows_valid = p->H; c2.data = p->spec.p;
+    c2.cplane = (long long)p->plane_elems(); c2.wiener = p->wiener.p; c2.K = p->K; c2.tw = p->tw_cols;
+    c2.mode = variant == 2 ? COL_FFT : variant == 3 ? COL_COPY : COL_WIENER;
+    c2.persistent_sms = (variant == 0) ? p->persistent_sms : 0;
+    c2.data_tiled = p->tiled; c2.wiener_tiled = p->tiled;
+    RowPassArgs r3{};
+    r3.n = p->Cp; r3.nrows = p->Rp; r3.npairs = npairs; r3.in_mode = ROW_IN_COMPLEX; r3.out_mode = ROW_OUT_REAL_PAIR;
+    r3.cin = p->spec.p; r3.cplane = (long long)p->plane_elems(); r3.units_total = nu; r3.raw = p->raw.p;
+    r3.raw_unit_stride = (long long)p->H * p->W; r3.raw_rows = p->H; r3.raw_cols = p->W; r3.minmax = p->mm.p; r3.local_units = nu;
+    r3.tw = p->tw_rows;
+    r3.tiled = p->tiled; r3.tile_shift = ilog2(col_pass_tile_width(p->Rp)); r3.tile_rows_shift = ilog2(p->Rp);
+    FDR_CUDA(launch_row_pass(r1, s));  // realistic data in the workspace
+    FDR_CUDA(launch_minmax_reset(p->mm.p, nu, s));
+    auto run = [&]() -> cudaError_t {
+        if (pass == 1) return launch_row_pass(r1, s);
+        if (pass == 2) return launch_col_pass(c2, s);
+        return launch_row_pass(r3, s);
+    };
+    FDR_CUDA(run());
+    FDR_CUDA(cudaEventRecord(p->ev[0], s));
+    for (int i = 0; i < reps; ++i) FDR_CUDA(run());
+    FDR_CUDA(cudaEventRecord(p->ev[1], s));
+    FDR_CUDA(cudaEventSynchronize(p->ev[1]));
+    float ms = 0.f;
+    FDR_CUDA(cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]));
+    *ms_avg = ms / reps;
+    return FDR_OK;
+}
+
 static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* out, int col_mode) {
     if (!p || !plane || !out) return set_error(FDR_E_INVALID, "bad arguments");
     if (col_mode == COL_FILTER && !p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
@@ -692,6 +774,7 @@ static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* 
     c.cplane = (long long)p->plane_elems();
     c.wiener = p->wiener.p;
     c.tw = p->tw_cols;
+    c.wiener_tiled = p->tiled;
     FDR_CUDA(launch_col_pass(c, s));
     FDR_CUDA(cudaMemcpyAsync(out, p->spec.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost, s));
     FDR_CUDA(cudaStreamSynchronize(s));

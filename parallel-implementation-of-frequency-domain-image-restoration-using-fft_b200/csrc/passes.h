@@ -23,7 +23,7 @@ namespace fdr {
 // (/root/reference/fft/fft_mpi.cpp:170-279) is thereby fused into the row passes.
 enum RowInMode { ROW_IN_PAIR_F32 = 0, ROW_IN_PAIR_U8 = 1, ROW_IN_COMPLEX = 2, ROW_IN_GATHER = 3 };
 enum RowOutMode { ROW_OUT_COMPLEX = 0, ROW_OUT_REAL_PAIR = 1, ROW_OUT_SCATTER = 2 };
-enum ColMode { COL_FFT = 0, COL_WIENER = 1, COL_MAKE_WIENER = 2, COL_FILTER = 3 };
+enum ColMode { COL_FFT = 0, COL_WIENER = 1, COL_MAKE_WIENER = 2, COL_FILTER = 3, COL_COPY = 4 /* timing probe: load + store only */ };
 
 struct RowPassArgs {
     int n;               // transform length (padded columns), power of two
@@ -43,6 +43,9 @@ struct RowPassArgs {
     long long units_total;       // global unit count (a pair's second unit may not exist)
     // ---- complex input / output ----
     const float2* cin;           // pair p at cin + p*cplane, row r at + r*n
+    int tiled;                   // complex planes: 0 = row-major; 1 = column-tiled layout
+    int tile_shift;              //   [col >> k][row][col & (2^k - 1)], k = tile_shift,
+    int tile_rows_shift;         //   rows_padded = 1 << tile_rows_shift
     float2* cout;
     long long cplane;
     // ---- real-pair output (pass 3) ----
@@ -67,10 +70,13 @@ struct ColPassArgs {
     const float2* tw;     // twiddle table of length n
     int rows_valid;       // rows >= rows_valid are read as zero (pass 1 skipped them)
     float2* data;         // in place; pair p at data + p*cplane
+    int data_tiled;       // 1: data is in the column-tiled layout [col/CW][row][col%CW] (CW = this length's tile width)
+    int wiener_tiled;     // 1: the Wiener factor (read or written) is in that layout
     long long cplane;
     const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
     float2* wiener_out;   // COL_MAKE_WIENER
     float K;
+    int persistent_sms;   // COL_WIENER: > 0 selects the persistent cp.async kernel with this many CTAs
 };
 
 // Launchers (defined in passes_*.cu).  Return cudaGetLastError() of the launch.

@@ -25,6 +25,27 @@ template <int LOGN> struct RowGeom {
     static constexpr size_t SMEM = fft_smem_bytes<N>(RPC);
 };
 
+// Element (row, x) of a complex plane: row-major, or column-tiled [x >> k][row][x & (2^k-1)].
+__device__ __forceinline__ long long tiled_offset(const RowPassArgs& a, int row, int x) {
+    const int k = a.tile_shift;
+    return ((((long long)(x >> k) << a.tile_rows_shift) + row) << k) + (x & ((1 << k) - 1));
+}
+// Thread t of a row touches x = t + T*m.  When T is a multiple of the tile width the m-th element is
+// off0 + m*step; otherwise step = -1 and the caller evaluates tiled_offset per element.
+template <int N> __device__ __forceinline__ void complex_plane_addressing(const RowPassArgs& a, int row, int t, long long& off0, long long& step) {
+    constexpr int T = FftGeom<N>::T;
+    if (!a.tiled) {
+        off0 = (long long)row * N + t;
+        step = T;
+    } else if ((T >> a.tile_shift) << a.tile_shift == T && T >= (1 << a.tile_shift)) {
+        off0 = tiled_offset(a, row, t);
+        step = (long long)T << a.tile_rows_shift;
+    } else {
+        off0 = 0;
+        step = -1;
+    }
+}
+
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
 __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const RowPassArgs a) {
     using Gm = RowGeom<LOGN>;
@@ -43,11 +64,13 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
 
     float2 v[E];
     if constexpr (IN_MODE == ROW_IN_COMPLEX) {
-        const float2* src = a.cin + (long long)pair * a.cplane + (long long)row * N + t;
+        long long off0, step;
+        complex_plane_addressing<N>(a, row, t, off0, step);
+        const float2* src = a.cin + (long long)pair * a.cplane + off0;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             float2 z = make_float2(0.f, 0.f);
-            if (active) z = src[T * m];
+            if (active) z = (step >= 0) ? src[m * step] : a.cin[(long long)pair * a.cplane + tiled_offset(a, row, t + T * m)];
             if constexpr (CONJ) z.y = -z.y;
             v[m] = z;
         }
@@ -114,12 +137,17 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
         }
     } else if constexpr (OUT_MODE == ROW_OUT_COMPLEX) {
         if (active) {
-            float2* dst = a.cout + (long long)pair * a.cplane + (long long)row * N + t;
+            long long off0, step;
+            complex_plane_addressing<N>(a, row, t, off0, step);
+            float2* dst = a.cout + (long long)pair * a.cplane + off0;
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 float2 z = v[m];
                 if constexpr (CONJ) z.y = -z.y;
-                dst[T * m] = z;
+                if (step >= 0)
+                    dst[m * step] = z;
+                else
+                    a.cout[(long long)pair * a.cplane + tiled_offset(a, row, t + T * m)] = z;
             }
         }
     } else {
@@ -216,8 +244,12 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
     const int c = tid % CW, t = tid / CW;
     const int col = blockIdx.x * CW + c;
     const bool active = col < a.pitch;
-    const long long stride = (long long)T * a.pitch;
-    float2* base = a.data + (long long)blockIdx.y * a.cplane + (long long)t * a.pitch + col;
+    // row-major: element (r, col) at r*pitch + col; column-tiled: (group*n + r)*CW + c, contiguous per CTA
+    const long long stride = a.data_tiled ? (long long)T * CW : (long long)T * a.pitch;
+    const long long first = a.data_tiled ? ((long long)blockIdx.x * N + t) * CW + c : (long long)t * a.pitch + col;
+    const long long wstride = a.wiener_tiled ? (long long)T * CW : (long long)T * a.pitch;
+    const long long wfirst = a.wiener_tiled ? ((long long)blockIdx.x * N + t) * CW + c : (long long)t * a.pitch + col;
+    float2* base = a.data + (long long)blockIdx.y * a.cplane + first;
 
     float2 v[E];
 #pragma unroll
@@ -228,37 +260,37 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
         v[m] = z;
     }
 
-    fft_forward<N, CW>(v, ex, a.tw, t, c);
+    if constexpr (MODE != COL_COPY) fft_forward<N, CW>(v, ex, a.tw, t, c);
 
     if constexpr (MODE == COL_WIENER) {
-        const float2* wf = a.wiener + (long long)t * a.pitch + col;
+        const float2* wf = a.wiener + wfirst;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             float2 w = make_float2(0.f, 0.f);
-            if (active) w = __ldg(wf + m * stride);
+            if (active) w = __ldg(wf + m * wstride);
             const float2 y = cmul(v[m], w);
             v[m] = make_float2(y.x, -y.y);
         }
         fft_forward<N, CW>(v, ex, a.tw, t, c);
     }
     if constexpr (MODE == COL_FILTER) {
-        const float2* wf = a.wiener + (long long)t * a.pitch + col;
+        const float2* wf = a.wiener + wfirst;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             float2 w = make_float2(0.f, 0.f);
-            if (active) w = __ldg(wf + m * stride);
+            if (active) w = __ldg(wf + m * wstride);
             v[m] = cmul(v[m], w);
         }
     }
 
     if (!active) return;
     if constexpr (MODE == COL_MAKE_WIENER) {
-        float2* wo = a.wiener_out + (long long)t * a.pitch + col;
+        float2* wo = a.wiener_out + wfirst;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const float hr = v[m].x, hi = v[m].y;
             const float denom = fmaf(hr, hr, hi * hi) + a.K;  // fft_serial.cpp:195-197
-            wo[m * stride] = make_float2(hr / denom, -hi / denom);
+            wo[m * wstride] = make_float2(hr / denom, -hi / denom);
         }
     } else {
 #pragma unroll
@@ -268,6 +300,116 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
             base[m * stride] = z;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------
+// Persistent column pass (COL_WIENER only; N*CW*8 B = 64 KB tiles, N <= 4096).
+// One CTA per SM walks a contiguous range of (column group, pair) work items, group-major:
+//   * the Wiener-factor tile of the group is fetched ONCE into shared memory (cp.async) and reused
+//     for every pair of the group -- Wf traffic drops from 8 B to 8/pairs B per pixel;
+//   * the next item's data tile is prefetched with cp.async into a staging buffer while the
+//     current tile is transformed in registers, so global-load latency is off the critical path;
+//   * results go straight from registers to global memory (fire-and-forget stores).
+// Shared memory: staging tile + Wiener tile + exchange buffer = 3 x 64 KB.
+// ---------------------------------------------------------------------------------
+template <int LOGN> struct ColPersistGeom {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int E = FftGeom<N>::E;
+    static constexpr int T = FftGeom<N>::T;
+    static constexpr int CW = (N >= 256) ? (8192 / N) : 32;
+    static constexpr int THREADS = T * CW;
+    static constexpr size_t TILE = (size_t)N * CW * sizeof(float2);
+    static constexpr size_t SMEM = 3 * TILE;
+    static constexpr int CHUNKS_PER_ROW = CW * 8 / 16;  // 16-byte cp.async chunks per tile row
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int LOGN>
+__global__ void __launch_bounds__(ColPersistGeom<LOGN>::THREADS, 1) col_wiener_persistent_kernel(const ColPassArgs a) {
+    using Gm = ColPersistGeom<LOGN>;
+    constexpr int N = Gm::N, E = Gm::E, T = Gm::T, CW = Gm::CW, CPR = Gm::CHUNKS_PER_ROW;
+    extern __shared__ float2 smem2[];
+    float2* stage = smem2;                    // [N][CW] next tile
+    float2* wsm = smem2 + (size_t)N * CW;     // [N][CW] Wiener tile of the current group
+    float2* ex = smem2 + (size_t)2 * N * CW;  // exchange buffer
+    const int tid = threadIdx.x;
+    const int c = tid % CW, t = tid / CW;
+    const int ngroups = a.pitch / CW;
+    const long long items = (long long)ngroups * a.npairs;
+    const long long i0 = items * blockIdx.x / gridDim.x, i1 = items * (blockIdx.x + 1) / gridDim.x;
+    if (i0 >= i1) return;
+    const long long stride = (long long)T * a.pitch;
+
+    auto issue_tile = [&](float2* dst, const float2* src_plane, int group, int rows) {
+        // rows x CW tile at columns [group*CW, +CW): CPR 16-byte chunks per row
+        const float2* src = src_plane + (long long)group * CW;
+        for (int q = tid; q < rows * CPR; q += Gm::THREADS) {
+            const int row = q / CPR, part = q % CPR;
+            cp_async16(dst + (size_t)row * CW + part * 2, src + (long long)row * a.pitch + part * 2);
+        }
+    };
+
+    int cur_group = -1;
+    {
+        const int g = (int)(i0 / a.npairs), p = (int)(i0 % a.npairs);
+        issue_tile(stage, a.data + (long long)p * a.cplane, g, a.rows_valid);
+    }
+    for (long long i = i0; i < i1; ++i) {
+        const int g = (int)(i / a.npairs), p = (int)(i % a.npairs);
+        if (g != cur_group) {
+            issue_tile(wsm, a.wiener, g, N);
+            cur_group = g;
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        float2 v[E];
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int r = t + T * m;
+            v[m] = (r < a.rows_valid) ? stage[(size_t)r * CW + c] : make_float2(0.f, 0.f);
+        }
+        __syncthreads();  // staging buffer free again
+        if (i + 1 < i1) {
+            const int g2 = (int)((i + 1) / a.npairs), p2 = (int)((i + 1) % a.npairs);
+            issue_tile(stage, a.data + (long long)p2 * a.cplane, g2, a.rows_valid);
+            cp_async_commit();
+        }
+        fft_forward<N, CW>(v, ex, a.tw, t, c);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const float2 w = wsm[(size_t)(t + T * m) * CW + c];
+            const float2 y = cmul(v[m], w);
+            v[m] = make_float2(y.x, -y.y);
+        }
+        fft_forward<N, CW>(v, ex, a.tw, t, c);
+        float2* base = a.data + (long long)p * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
+#pragma unroll
+        for (int m = 0; m < E; ++m) base[m * stride] = v[m];
+    }
+}
+
+template <int LOGN> cudaError_t launch_col_wiener_persistent(const ColPassArgs& a, int num_sms, cudaStream_t s) {
+    using Gm = ColPersistGeom<LOGN>;
+    static unsigned long long configured = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured >> (dev & 63) & 1ULL)) {
+        cudaError_t e = cudaFuncSetAttribute(col_wiener_persistent_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+        if (e != cudaSuccess) return e;
+        configured |= 1ULL << (dev & 63);
+    }
+    const long long items = (long long)(a.pitch / Gm::CW) * a.npairs;
+    int grid = num_sms;
+    if (grid > items) grid = (int)items;
+    col_wiener_persistent_kernel<LOGN><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
+    return cudaGetLastError();
 }
 
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row_variant(const RowPassArgs& a, cudaStream_t s) {
@@ -324,9 +466,15 @@ template <int LOGN, int CW> cudaError_t launch_col_pass_t(const ColPassArgs& a, 
     switch (a.mode) {
         case COL_FFT:
             return a.conj ? launch_col_variant<LOGN, CW, COL_FFT, true>(a, s) : launch_col_variant<LOGN, CW, COL_FFT, false>(a, s);
-        case COL_WIENER: return launch_col_variant<LOGN, CW, COL_WIENER, false>(a, s);
+        case COL_WIENER:
+            if constexpr (LOGN >= 6 && LOGN <= 12) {
+                if (a.persistent_sms > 0 && !a.data_tiled && !a.wiener_tiled && a.pitch % ColPersistGeom<LOGN>::CW == 0)
+                    return launch_col_wiener_persistent<LOGN>(a, a.persistent_sms, s);
+            }
+            return launch_col_variant<LOGN, CW, COL_WIENER, false>(a, s);
         case COL_MAKE_WIENER: return launch_col_variant<LOGN, CW, COL_MAKE_WIENER, false>(a, s);
         case COL_FILTER: return launch_col_variant<LOGN, CW, COL_FILTER, false>(a, s);
+        case COL_COPY: return launch_col_variant<LOGN, CW, COL_COPY, false>(a, s);
     }
     return cudaErrorInvalidValue;
 }

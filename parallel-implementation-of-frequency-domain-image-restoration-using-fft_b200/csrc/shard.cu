@@ -52,6 +52,7 @@ struct fdr_shard {
     const float2* tw_rows = nullptr;
     const float2* tw_cols = nullptr;
     long long launches = 0;
+    int persistent_sms = 0;
 };
 
 namespace {
@@ -126,6 +127,12 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
     if (r1 > rows) r1 = rows;
     s->rows_local = r1 > s->row0 ? r1 - s->row0 : 0;
     s->npairs = (channels + 1) / 2;
+    {
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const char* env = getenv("FDR_COL_PERSISTENT");
+        s->persistent_sms = (env && atoi(env) != 0) ? sms : 0;
+    }
     int rc = FDR_OK;
     cudaError_t e = get_twiddles(Cp, &s->tw_rows);
     if (e == cudaSuccess) e = get_twiddles(Rp, &s->tw_cols);
@@ -294,6 +301,7 @@ FDR_API int fdr_shard_phase2_cols(fdr_shard* s, void* stream) {
     c.wiener = s->wiener.p;
     c.K = s->K;
     c.tw = s->tw_cols;
+    c.persistent_sms = s->persistent_sms;
     FDR_CUDA(launch_col_pass(c, pick(s, stream)));
     s->launches += 1;
     return FDR_OK;

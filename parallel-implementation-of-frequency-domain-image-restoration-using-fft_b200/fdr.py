@@ -63,6 +63,7 @@ def lib():
             "fdr_plan_last_minmax_host": [vp, _fp, i],
             "fdr_plan_get_profile": [vp, _fp],
             "fdr_plan_last_launch_count": [vp, C.POINTER(ll)],
+            "fdr_plan_time_pass": [vp, i, i, i, i, _fp],
             "fdr_plan_set_kernel_timing": [vp, i],
             "fdr_plan_get_kernel_timing": [vp, C.POINTER(d), C.POINTER(ll), C.POINTER(d)],
             "fdr_plan_forward_spectrum_host": [vp, _fp, sz, _fp],
@@ -229,6 +230,11 @@ class Plan:
         n = C.c_longlong(0)
         _check(lib().fdr_plan_last_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def time_pass(self, which, variant=0, npairs=3, reps=10):
+        ms = C.c_float(0)
+        _check(lib().fdr_plan_time_pass(self.h, which, variant, npairs, reps, C.byref(ms)))
+        return ms.value
 
     def set_kernel_timing(self, on=True):
         _check(lib().fdr_plan_set_kernel_timing(self.h, int(on)))
