@@ -39,15 +39,6 @@ int ensure_device(int device) {
     return FDR_OK;
 }
 
-bool is_pinned_or_device(const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-}
-
 }  // namespace
 
 struct fdr_plan {
@@ -59,6 +50,8 @@ struct fdr_plan {
     int psf_rows = 0, psf_cols = 0;
     bool have_wiener = false;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the pipelined host path
+    cudaEvent_t ev_in[2] = {}, ev_cmp[2] = {}, ev_out[2] = {};
     cudaEvent_t ev[8] = {};
     // device workspace
     DevBuf<float2> spec;          // chunk pairs x Rp x Cp
@@ -447,6 +440,13 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
         cudaEventDestroy(r.b);
     }
     for (auto e : p->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+        if (p->ev_cmp[i]) cudaEventDestroy(p->ev_cmp[i]);
+        if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+    }
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return FDR_OK;
@@ -598,45 +598,67 @@ __attribute__((visibility("default"))) int fdr_restore_planes_host_f32(fdr_plan*
     return FDR_OK;
 }
 
+// Whole images through host buffers, pipelined: the batch is cut into chunks and the H2D copy of
+// chunk k+1, the restoration of chunk k and the D2H copy of chunk k-1 run concurrently on three
+// streams (PCIe is full duplex), with double-buffered device staging.  The reference does
+// memcpy -> H2D -> compute -> D2H -> sync serially per channel (fft_gpu.cu:347-349,373-374).
 __attribute__((visibility("default"))) int fdr_restore_images_host_u8(fdr_plan* p, const uint8_t* in_images, uint8_t* out_images, int n_images) {
     if (!p || !in_images || !out_images || n_images < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set: call fdr_plan_set_psf_* first");
     FDR_TRY(ensure_device(p->device));
-    const size_t bytes = (size_t)p->H * p->W * p->C * n_images;
-    cudaStream_t s = p->stream;
+    const size_t img_bytes = (size_t)p->H * p->W * p->C;
+    const int chunk = p->chunk_images(n_images);
+    const size_t chunk_bytes = img_bytes * chunk;
     for (int i = 0; i < 6; ++i) p->profile_ms[i] = 0.f;
-    FDR_TRY(p->d_in_u8.ensure(bytes));
-    FDR_TRY(p->d_out_u8.ensure(bytes));
-    const uint8_t* src = in_images;
-    uint8_t* dst = out_images;
-    const bool in_direct = is_pinned_or_device(in_images), out_direct = is_pinned_or_device(out_images);
-    if (!in_direct) {
-        FDR_TRY(p->h_u8_in.ensure(bytes));
-        memcpy(p->h_u8_in.p, in_images, bytes);
-        src = p->h_u8_in.p;
-    }
-    if (!out_direct) {
-        FDR_TRY(p->h_u8_out.ensure(bytes));
-        dst = p->h_u8_out.p;
+    if (!p->s_in) {
+        FDR_CUDA(cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+        FDR_CUDA(cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            FDR_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+            FDR_CUDA(cudaEventCreateWithFlags(&p->ev_cmp[i], cudaEventDisableTiming));
+            FDR_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+        }
     }
     {
-        ScopedTimer t(p, 1, s, &p->profile_ms[1]);
-        FDR_CUDA(cudaMemcpyAsync(p->d_in_u8.p, src, bytes, cudaMemcpyHostToDevice, s));
+        ScopedTimer t(p, 0, p->stream, &p->profile_ms[0]);
+        FDR_TRY(p->d_in_u8.ensure(2 * chunk_bytes));
+        FDR_TRY(p->d_out_u8.ensure(2 * chunk_bytes));
+        FDR_TRY(ensure_workspace(p, chunk * p->C));
         t.stop();
     }
-    {
-        ScopedTimer t(p, 2, s, &p->profile_ms[3]);
+    cudaStream_t s_in = p->s_in, s_cmp = p->stream, s_out = p->s_out;
+    FDR_CUDA(cudaEventRecord(p->ev[2], s_cmp));  // wall span of the pipelined region (bucket 4: compute)
+    long long launches = 0;
+    int k = 0;
+    for (int first = 0; first < n_images; first += chunk, ++k) {
+        const int n = (n_images - first < chunk) ? (n_images - first) : chunk;
+        const int b = k & 1;
+        const size_t off = img_bytes * first, bytes = img_bytes * n;
+        uint8_t* din = p->d_in_u8.p + (size_t)b * chunk_bytes;
+        uint8_t* dout = p->d_out_u8.p + (size_t)b * chunk_bytes;
+        if (k >= 2) FDR_CUDA(cudaStreamWaitEvent(s_in, p->ev_cmp[b], 0));  // chunk k-2 no longer reads din
+        FDR_CUDA(cudaMemcpyAsync(din, in_images + off, bytes, cudaMemcpyHostToDevice, s_in));
+        FDR_CUDA(cudaEventRecord(p->ev_in[b], s_in));
+        FDR_CUDA(cudaStreamWaitEvent(s_cmp, p->ev_in[b], 0));
+        if (k >= 2) FDR_CUDA(cudaStreamWaitEvent(s_cmp, p->ev_out[b], 0));  // chunk k-2's D2H has drained dout
         InputDesc in;
         in.mode = ROW_IN_PAIR_U8;
-        in.u8 = p->d_in_u8.p;
-        FDR_TRY(restore_units_device(p, in, nullptr, p->d_out_u8.p, (long long)n_images * p->C, s));
-        t.stop();
+        in.u8 = din;
+        FDR_TRY(restore_units_device(p, in, nullptr, dout, (long long)n * p->C, s_cmp));
+        launches += p->launches;
+        FDR_CUDA(cudaEventRecord(p->ev_cmp[b], s_cmp));
+        FDR_CUDA(cudaStreamWaitEvent(s_out, p->ev_cmp[b], 0));
+        FDR_CUDA(cudaMemcpyAsync(out_images + off, dout, bytes, cudaMemcpyDeviceToHost, s_out));
+        FDR_CUDA(cudaEventRecord(p->ev_out[b], s_out));
     }
-    {
-        ScopedTimer t(p, 3, s, &p->profile_ms[4]);
-        FDR_CUDA(cudaMemcpyAsync(dst, p->d_out_u8.p, bytes, cudaMemcpyDeviceToHost, s));
-        t.stop();
-    }
-    if (!out_direct) memcpy(out_images, p->h_u8_out.p, bytes);
+    FDR_CUDA(cudaStreamSynchronize(s_out));
+    FDR_CUDA(cudaStreamSynchronize(s_in));
+    FDR_CUDA(cudaEventRecord(p->ev[3], s_cmp));
+    FDR_CUDA(cudaEventSynchronize(p->ev[3]));
+    float ms = 0.f;
+    FDR_CUDA(cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]));
+    p->profile_ms[3] = ms;  // H2D, compute and D2H overlap: reported as one bucket
+    p->launches = launches;
     return FDR_OK;
 }
 
