@@ -407,6 +407,11 @@ def main():
     launches_per_step = plan.last_launch_count()
     ktimes = plan.kernel_timing()
     plan.set_kernel_timing(False)
+    # the same kernels timed ALONE (no other chunk in flight), CUDA events inside the library
+    iso_pairs = 3
+    isolated = {"pairs_per_launch": iso_pairs,
+                "pass1_ms": plan.time_pass(1, 0, iso_pairs, 10), "pass2_ms": plan.time_pass(2, 0, iso_pairs, 10),
+                "pass3_ms": plan.time_pass(3, 0, iso_pairs, 10)}
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -464,6 +469,9 @@ def main():
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src + " (of measured)",
         "bytes_per_launch": kd["bytes"] / max(kd["launches"], 1), "ms_per_launch": kd["ms"] / max(kd["launches"], 1),
         "kernel_share_of_step": kd["ms"] / ksum if ksum else None,
+        "concurrency": "chunks run on %s streams; per-launch times include overlap with other chunks' kernels" % os.environ.get("FDR_LANES", "4"),
+        "isolated": dict(isolated, pass2_GBps=(8.0 * H * W + 16.0 * plan.padded[0] * plan.padded[1]) * iso_pairs / (isolated["pass2_ms"] * 1e-3) / 1e9,
+                         pass2_frac=(8.0 * H * W + 16.0 * plan.padded[0] * plan.padded[1]) * iso_pairs / (isolated["pass2_ms"] * 1e-3) / 1e9 / peak),
         "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                         "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0)} for k, v in ktimes.items()},
         "pipeline": {

@@ -62,6 +62,11 @@ struct fdr_plan {
     DevBuf<float2> wiener;        // Rp x Cp
     DevBuf<float> psf;            // psf_rows x psf_cols
     int persistent_sms = 0;           // SM count when the persistent column kernel is enabled
+    int lanes = 4;                    // chunks in flight on separate streams (FDR_LANES=1..4)
+    cudaStream_t lane_stream[4] = {};
+    cudaEvent_t lane_fork = nullptr, lane_join[4] = {};
+    int last_lane = 0;
+    int ws_units = 0;                 // per-lane workspace capacity in units
     int tiled = 0;                    // column-tiled spectrum/Wiener layout inside the restore pipeline (FDR_TILED=1)
     const float2* tw_rows = nullptr;  // twiddles for length Cp (row passes)
     const float2* tw_cols = nullptr;  // twiddles for length Rp (column passes)
@@ -143,12 +148,22 @@ struct KernelTimer {  // records an event pair around one launch when kernel tim
 };
 
 int ensure_workspace(fdr_plan* p, int chunk_units) {
+    if (chunk_units < p->ws_units) chunk_units = p->ws_units;  // lane offsets must stay valid: capacity only grows
     const int pairs = (chunk_units + 1) / 2;
-    FDR_TRY(p->spec.ensure((size_t)pairs * p->plane_elems()));
-    FDR_TRY(p->raw.ensure((size_t)chunk_units * p->H * p->W));
-    FDR_TRY(p->mm.ensure((size_t)chunk_units * 2));
-    FDR_TRY(p->ss.ensure((size_t)chunk_units));
-    FDR_TRY(p->mmf.ensure((size_t)chunk_units * 2));
+    const size_t L = (size_t)p->lanes;
+    FDR_TRY(p->spec.ensure(L * pairs * p->plane_elems()));
+    FDR_TRY(p->raw.ensure(L * chunk_units * p->H * p->W));
+    FDR_TRY(p->mm.ensure(L * chunk_units * 2));
+    FDR_TRY(p->ss.ensure(L * chunk_units));
+    FDR_TRY(p->mmf.ensure(L * chunk_units * 2));
+    p->ws_units = chunk_units;
+    if (p->lanes > 1 && !p->lane_fork) {
+        FDR_CUDA(cudaEventCreateWithFlags(&p->lane_fork, cudaEventDisableTiming));
+        for (int i = 0; i < p->lanes; ++i) {
+            FDR_CUDA(cudaStreamCreateWithFlags(&p->lane_stream[i], cudaStreamNonBlocking));
+            FDR_CUDA(cudaEventCreateWithFlags(&p->lane_join[i], cudaEventDisableTiming));
+        }
+    }
     return FDR_OK;
 }
 
@@ -167,10 +182,26 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
     FDR_TRY(ensure_workspace(p, (int)chunk_units));
     p->launches = 0;
     const long long HW = (long long)p->H * p->W;
-    for (long long base = 0; base < n_units; base += chunk_units) {
+    const int L = (n_units > chunk_units) ? p->lanes : 1;  // several chunks in flight on separate streams
+    cudaStream_t s_caller = s;
+    if (L > 1) {
+        FDR_CUDA(cudaEventRecord(p->lane_fork, s_caller));
+        for (int i = 0; i < L; ++i) FDR_CUDA(cudaStreamWaitEvent(p->lane_stream[i], p->lane_fork, 0));
+    }
+    const size_t ws_pairs = (size_t)(p->ws_units + 1) / 2;
+    long long chunk_index = 0;
+    for (long long base = 0; base < n_units; base += chunk_units, ++chunk_index) {
         const int nu = (int)((n_units - base < chunk_units) ? (n_units - base) : chunk_units);
         const int np = (nu + 1) / 2;
-        FDR_CUDA(launch_minmax_reset(p->mm.p, nu, s));
+        const int lane = (int)(chunk_index % L);
+        if (L > 1) s = p->lane_stream[lane];
+        float2* const spec_l = p->spec.p + (size_t)lane * ws_pairs * p->plane_elems();
+        float* const raw_l = p->raw.p + (size_t)lane * p->ws_units * HW;
+        unsigned int* const mm_l = p->mm.p + (size_t)lane * p->ws_units * 2;
+        float2* const ss_l = p->ss.p + (size_t)lane * p->ws_units;
+        float* const mmf_l = p->mmf.p + (size_t)lane * p->ws_units * 2;
+        p->last_lane = lane;
+        FDR_CUDA(launch_minmax_reset(mm_l, nu, s));
         RowPassArgs r1{};
         r1.n = p->Cp;
         r1.nrows = p->H;
@@ -186,7 +217,7 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r1.img_cols = p->W;
         r1.unit_base = base;
         r1.units_total = n_units;
-        r1.cout = p->spec.p;
+        r1.cout = spec_l;
         r1.cplane = (long long)p->plane_elems();
         r1.tw = p->tw_rows;
         r1.tiled = p->tiled;
@@ -205,7 +236,7 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         c2.npairs = np;
         c2.mode = COL_WIENER;
         c2.rows_valid = p->H;
-        c2.data = p->spec.p;
+        c2.data = spec_l;
         c2.cplane = (long long)p->plane_elems();
         c2.wiener = p->wiener.p;
         c2.K = p->K;
@@ -224,15 +255,15 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r3.npairs = np;
         r3.in_mode = ROW_IN_COMPLEX;
         r3.out_mode = ROW_OUT_REAL_PAIR;
-        r3.cin = p->spec.p;
+        r3.cin = spec_l;
         r3.cplane = (long long)p->plane_elems();
         r3.unit_base = base;
         r3.units_total = n_units;
-        r3.raw = p->raw.p;
+        r3.raw = raw_l;
         r3.raw_unit_stride = HW;
         r3.raw_rows = p->H;
         r3.raw_cols = p->W;
-        r3.minmax = p->mm.p;
+        r3.minmax = mm_l;
         r3.local_units = nu;
         r3.tw = p->tw_rows;
         r3.tiled = p->tiled;
@@ -243,19 +274,25 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
             FDR_CUDA(launch_row_pass(r3, s));
         }
 
-        FDR_CUDA(launch_minmax_finalize(p->mm.p, p->ss.p, p->mmf.p, nu, s));
+        FDR_CUDA(launch_minmax_finalize(mm_l, ss_l, mmf_l, nu, s));
         p->launches += 5;
         if (out_u8) {
             KernelTimer kt(p, s, 3, 5.0 * HW * nu);
-            FDR_CUDA(launch_pack_u8(p->raw.p, HW, p->ss.p, out_u8 + base * HW, nu / C, C, p->H, p->W, s));
+            FDR_CUDA(launch_pack_u8(raw_l, HW, ss_l, out_u8 + base * HW, nu / C, C, p->H, p->W, s));
             p->launches += 1;
         }
         if (out_f32) {
             KernelTimer kt(p, s, 3, 8.0 * HW * nu);
-            FDR_CUDA(launch_normalize_f32(p->raw.p, HW, p->ss.p, out_f32 + base * HW, HW, nu, p->H, p->W, s));
+            FDR_CUDA(launch_normalize_f32(raw_l, HW, ss_l, out_f32 + base * HW, HW, nu, p->H, p->W, s));
             p->launches += 1;
         }
         p->last_units = nu;
+    }
+    if (L > 1) {
+        for (int i = 0; i < L; ++i) {
+            FDR_CUDA(cudaEventRecord(p->lane_join[i], p->lane_stream[i]));
+            FDR_CUDA(cudaStreamWaitEvent(s_caller, p->lane_join[i], 0));
+        }
     }
     return FDR_OK;
 }
@@ -396,6 +433,8 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const char* env = getenv("FDR_COL_PERSISTENT");
         p->persistent_sms = (env && atoi(env) != 0) ? sms : 0;  // opt-in: measured slower than 2 CTAs/SM
+        const char* ln = getenv("FDR_LANES");
+        if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) p->lanes = atoi(ln);
         const char* tl = getenv("FDR_TILED");
         if (tl) p->tiled = atoi(tl) != 0;
         if (p->Cp % col_pass_tile_width(p->Rp) != 0) p->tiled = 0;  // narrow images: plain row-major
@@ -445,6 +484,11 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
         if (p->ev_cmp[i]) cudaEventDestroy(p->ev_cmp[i]);
         if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
     }
+    for (int i = 0; i < 4; ++i) {
+        if (p->lane_stream[i]) cudaStreamDestroy(p->lane_stream[i]);
+        if (p->lane_join[i]) cudaEventDestroy(p->lane_join[i]);
+    }
+    if (p->lane_fork) cudaEventDestroy(p->lane_fork);
     if (p->s_in) cudaStreamDestroy(p->s_in);
     if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -665,9 +709,10 @@ __attribute__((visibility("default"))) int fdr_restore_images_host_u8(fdr_plan* 
 __attribute__((visibility("default"))) int fdr_plan_last_minmax_host(fdr_plan* p, float* minmax, int capacity_planes) {
     if (!p || !minmax) return set_error(FDR_E_INVALID, "bad arguments");
     FDR_CUDA(cudaSetDevice(p->device));
-    FDR_CUDA(cudaStreamSynchronize(p->stream));
+    FDR_CUDA(cudaDeviceSynchronize());
     int n = p->last_units < capacity_planes ? p->last_units : capacity_planes;
-    if (n > 0) FDR_CUDA(cudaMemcpy(minmax, p->mmf.p, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
+    if (n > 0)
+        FDR_CUDA(cudaMemcpy(minmax, p->mmf.p + (size_t)p->last_lane * p->ws_units * 2, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost));
     return FDR_OK;
 }
 
