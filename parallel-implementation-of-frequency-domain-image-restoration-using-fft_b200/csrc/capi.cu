@@ -59,7 +59,9 @@ struct fdr_plan {
     DevBuf<unsigned int> mm;      // chunk units x 2
     DevBuf<float2> ss;            // chunk units
     DevBuf<float> mmf;            // chunk units x 2
-    DevBuf<float2> wiener;        // Rp x Cp
+    DevBuf<float2> wiener;        // Rp x Cp (digit-swapped row order when col_split is set)
+    DevBuf<float2> wiener_nat;    // natural-order copy, built lazily for the parity-gate API of long-column plans
+    bool col_split = false;       // long columns: four-step column pass (col_split.cuh)
     DevBuf<float> psf;            // psf_rows x psf_cols
     int persistent_sms = 0;           // SM count when the persistent column kernel is enabled
     int lanes = 4;                    // chunks in flight on separate streams (FDR_LANES=1..4)
@@ -246,7 +248,13 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         c2.wiener_tiled = p->tiled;
         {
             KernelTimer kt(p, s, 1, (8.0 * p->H * p->Cp + 16.0 * P) * np);
-            FDR_CUDA(launch_col_pass(c2, s));
+            if (p->col_split) {
+                int nl = 0;
+                FDR_CUDA(launch_col_split(c2, s, &nl));
+                p->launches += nl - 1;
+            } else {
+                FDR_CUDA(launch_col_pass(c2, s));
+            }
         }
 
         RowPassArgs r3{};
@@ -297,10 +305,10 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
     return FDR_OK;
 }
 
-int build_wiener(fdr_plan* p) {
+int build_wiener_into(fdr_plan* p, DevBuf<float2>& dst, bool split) {
     if (p->psf_rows > p->Rp || p->psf_cols > p->Cp)
         return set_error(FDR_E_INVALID, "PSF %dx%d larger than the padded image %dx%d", p->psf_rows, p->psf_cols, p->Rp, p->Cp);
-    FDR_TRY(p->wiener.ensure(p->plane_elems()));
+    FDR_TRY(dst.ensure(p->plane_elems()));
     FDR_TRY(p->spec.ensure(p->plane_elems()));
     cudaStream_t s = p->stream;
     RowPassArgs r{};
@@ -329,13 +337,16 @@ int build_wiener(fdr_plan* p) {
     c.rows_valid = p->psf_rows;
     c.data = p->spec.p;
     c.cplane = (long long)p->plane_elems();
-    c.wiener_out = p->wiener.p;
+    c.wiener_out = dst.p;
     c.K = p->K;
     c.tw = p->tw_cols;
-    c.wiener_tiled = p->tiled;
-    FDR_CUDA(launch_col_pass(c, s));
+    if (split) {
+        FDR_CUDA(launch_col_split(c, s, nullptr));
+    } else {
+        c.wiener_tiled = p->tiled;
+        FDR_CUDA(launch_col_pass(c, s));
+    }
     FDR_CUDA(cudaStreamSynchronize(s));
-    p->have_wiener = true;
     return FDR_OK;
 }
 
@@ -354,6 +365,13 @@ struct ScopedTimer {  // event pair on a stream, accumulating into a bucket (Pro
         *dst += ms;
     }
 };
+
+int build_wiener(fdr_plan* p) {
+    p->wiener_nat.release();
+    FDR_TRY(build_wiener_into(p, p->wiener, p->col_split));
+    p->have_wiener = true;
+    return FDR_OK;
+}
 
 }  // namespace
 
@@ -433,6 +451,14 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         const char* env = getenv("FDR_COL_PERSISTENT");
         p->persistent_sms = (env && atoi(env) != 0) ? sms : 0;  // opt-in: measured slower than 2 CTAs/SM
+        {
+            ColPassArgs probe{};
+            probe.n = p->Rp;
+            probe.pitch = p->Cp;
+            probe.mode = COL_WIENER;
+            const char* cs = getenv("FDR_COL_SPLIT");
+            p->col_split = col_split_applicable(probe) && !(cs && atoi(cs) == 0);
+        }
         const char* ln = getenv("FDR_LANES");
         if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) p->lanes = atoi(ln);
         const char* tl = getenv("FDR_TILED");
@@ -463,6 +489,7 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
     p->ss.release();
     p->mmf.release();
     p->wiener.release();
+    p->wiener_nat.release();
     p->psf.release();
     p->d_in_u8.release();
     p->d_out_u8.release();
@@ -552,6 +579,17 @@ __attribute__((visibility("default"))) int fdr_plan_get_wiener_host(const fdr_pl
     if (!p || !wf) return set_error(FDR_E_INVALID, "bad arguments");
     if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
     FDR_CUDA(cudaSetDevice(p->device));
+    if (p->col_split) {
+        // stored with digit-swapped rows: row 128*k1 + k2 holds frequency k1 + (Rp/128)*k2 (layout conversion only)
+        std::vector<float2> tmp(p->plane_elems());
+        FDR_CUDA(cudaMemcpy(tmp.data(), p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
+        float2* out = reinterpret_cast<float2*>(wf);
+        const int n1 = p->Rp / 128;
+        for (int k1 = 0; k1 < n1; ++k1)
+            for (int k2 = 0; k2 < 128; ++k2)
+                memcpy(out + (size_t)(k1 + n1 * k2) * p->Cp, tmp.data() + (size_t)(128 * k1 + k2) * p->Cp, sizeof(float2) * p->Cp);
+        return FDR_OK;
+    }
     if (!p->tiled) {
         FDR_CUDA(cudaMemcpy(wf, p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
         return FDR_OK;
@@ -790,7 +828,7 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     FDR_CUDA(launch_minmax_reset(p->mm.p, nu, s));
     auto run = [&]() -> cudaError_t {
         if (pass == 1) return launch_row_pass(r1, s);
-        if (pass == 2) return launch_col_pass(c2, s);
+        if (pass == 2) return (p->col_split && c2.mode == COL_WIENER) ? launch_col_split(c2, s, nullptr) : launch_col_pass(c2, s);
         return launch_row_pass(r3, s);
     };
     FDR_CUDA(run());
@@ -842,6 +880,15 @@ static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* 
     c.wiener = p->wiener.p;
     c.tw = p->tw_cols;
     c.wiener_tiled = p->tiled;
+    if (col_mode == COL_FILTER && p->col_split) {
+        if (!p->wiener_nat.p) {
+            // the row pass above wrote the image spectrum into spec; build the natural-order factor first
+            FDR_TRY(build_wiener_into(p, p->wiener_nat, false));
+            FDR_CUDA(launch_row_pass(r, s));
+        }
+        c.wiener = p->wiener_nat.p;
+        c.wiener_tiled = 0;
+    }
     FDR_CUDA(launch_col_pass(c, s));
     FDR_CUDA(cudaMemcpyAsync(out, p->spec.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost, s));
     FDR_CUDA(cudaStreamSynchronize(s));

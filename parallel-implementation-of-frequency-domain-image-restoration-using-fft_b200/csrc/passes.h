@@ -84,6 +84,10 @@ cudaError_t launch_row_pass(const RowPassArgs& a, cudaStream_t s);
 cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s);
 // Twiddle table for power-of-two length n on the current device (cached).
 cudaError_t get_twiddles(int n, const float2** out);
+// Long columns (n = 8192, 16384), COL_WIENER / COL_MAKE_WIENER: four-step column pass (col_split.cuh).
+// The Wiener factor it reads/writes is in digit-swapped row order: row 128*k1 + k2 holds frequency k1 + (n/128)*k2.
+bool col_split_applicable(const ColPassArgs& a);
+cudaError_t launch_col_split(const ColPassArgs& a, cudaStream_t s, int* launches);
 // Tile width (columns per CTA) the column pass uses for length n.
 int col_pass_tile_width(int n);
 

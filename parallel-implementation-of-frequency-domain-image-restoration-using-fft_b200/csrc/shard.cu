@@ -53,6 +53,7 @@ struct fdr_shard {
     const float2* tw_cols = nullptr;
     long long launches = 0;
     int persistent_sms = 0;
+    bool col_split = false;
 };
 
 namespace {
@@ -93,7 +94,10 @@ int build_wiener(fdr_shard* s) {
     c.wiener_out = s->wiener.p;
     c.K = s->K;
     c.tw = s->tw_cols;
-    FDR_CUDA(launch_col_pass(c, st));
+    if (s->col_split)
+        FDR_CUDA(launch_col_split(c, st, nullptr));
+    else
+        FDR_CUDA(launch_col_pass(c, st));
     FDR_CUDA(cudaStreamSynchronize(st));
     s->have_wiener = true;
     return FDR_OK;
@@ -127,6 +131,14 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
     if (r1 > rows) r1 = rows;
     s->rows_local = r1 > s->row0 ? r1 - s->row0 : 0;
     s->npairs = (channels + 1) / 2;
+    {
+        ColPassArgs probe{};
+        probe.n = Rp;
+        probe.pitch = Cp / world;
+        probe.mode = COL_WIENER;
+        const char* cs = getenv("FDR_COL_SPLIT");
+        s->col_split = col_split_applicable(probe) && !(cs && atoi(cs) == 0);
+    }
     {
         int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -302,8 +314,14 @@ FDR_API int fdr_shard_phase2_cols(fdr_shard* s, void* stream) {
     c.K = s->K;
     c.tw = s->tw_cols;
     c.persistent_sms = s->persistent_sms;
-    FDR_CUDA(launch_col_pass(c, pick(s, stream)));
-    s->launches += 1;
+    if (s->col_split) {
+        int nl = 0;
+        FDR_CUDA(launch_col_split(c, pick(s, stream), &nl));
+        s->launches += nl;
+    } else {
+        FDR_CUDA(launch_col_pass(c, pick(s, stream)));
+        s->launches += 1;
+    }
     return FDR_OK;
 }
 

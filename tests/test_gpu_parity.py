@@ -119,7 +119,9 @@ def test_wiener_factor(gpu, oracle):
 
 
 RESTORE_CASES = [(48, 80, 9, 30.0), (64, 64, 5, 10.0), (100, 200, 21, 45.0), (7, 9, 3, 20.0), (1, 33, 1, 0.0),
-                 (33, 1, 1, 0.0), (1, 1, 1, 0.0), (256, 256, 50, 30.0), (330, 640, 40, 45.0), (17, 300, 15, 123.4)]
+                 (33, 1, 1, 0.0), (1, 1, 1, 0.0), (256, 256, 50, 30.0), (330, 640, 40, 45.0), (17, 300, 15, 123.4),
+                 # long columns: four-step column pass (col_split), 8192 = 64*128 and 16384 = 128*128
+                 (8192, 48, 9, 30.0), (5000, 100, 21, 45.0), (16384, 40, 5, 10.0), (9000, 16, 3, 20.0)]
 
 
 @pytest.mark.parametrize("H,W,S,ang", RESTORE_CASES)
@@ -162,6 +164,19 @@ def test_restore_golden_reference_outputs(gpu):
             G = p.forward_spectrum(img)
         assert rel_l2(G, g[name + "_G"]) < SPECTRUM_TOL
         assert np.abs(out - g[name + "_norm"][: img.shape[0], : img.shape[1]]).max() < 1e-4
+
+
+def test_wiener_factor_long_columns(gpu, oracle):
+    """Plans with 8192/16384 rows keep Wf in digit-swapped row order; the inspection call hands it
+    back in natural order."""
+    psf = oracle.port().motion_psf(9, 30.0)
+    with gpu.Plan(8192, 32, 1) as p:
+        p.set_psf(psf, K)
+        wf = p.get_wiener()
+    hp = np.zeros((8192, 32))
+    hp[:9, :9] = psf
+    H = np.fft.fft2(hp)
+    assert rel_l2(wf, np.conj(H) / (np.abs(H) ** 2 + np.float32(K))) < 2e-6
 
 
 def test_errors(gpu, oracle):

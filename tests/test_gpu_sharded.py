@@ -53,7 +53,8 @@ def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang):
             s.close()
 
 
-@pytest.mark.parametrize("H,W,world", [(200, 320, 2), (200, 320, 4), (256, 512, 8), (64, 1024, 2), (1000, 40, 4), (33, 70, 8)])
+@pytest.mark.parametrize("H,W,world", [(200, 320, 2), (200, 320, 4), (256, 512, 8), (64, 1024, 2), (1000, 40, 4), (33, 70, 8),
+                                       (8192, 64, 2), (16384, 128, 8)])
 def test_sharded_equals_single_gpu_and_oracle(gpu, oracle, H, W, world):
     torch = pytest.importorskip("torch")
     img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 0, H, W), (1, 2, 0)))
