@@ -635,24 +635,21 @@ __attribute__((visibility("default"))) int fdr_restore_planes_host_f32(fdr_plan*
     if (in_stride == 0) in_stride = rowb;
     if (out_stride == 0) out_stride = rowb;
     if (in_stride < rowb || out_stride < rowb) return set_error(FDR_E_INVALID, "row stride smaller than a row");
+    for (int u = 0; u < n_planes; ++u)
+        if (!in_planes[u] || !out_planes[u]) return set_error(FDR_E_INVALID, "plane %d is NULL", u);
     cudaStream_t s = p->stream;
     for (int i = 0; i < 6; ++i) p->profile_ms[i] = 0.f;
     {
         ScopedTimer t(p, 0, s, &p->profile_ms[0]);
         FDR_TRY(p->d_in_f32.ensure(HW * n_planes));
         FDR_TRY(p->d_out_f32.ensure(HW * n_planes));
-        FDR_TRY(p->h_f32_in.ensure(HW * n_planes));
-        FDR_TRY(p->h_f32_out.ensure(HW * n_planes));
         t.stop();
     }
     {
+        // straight from the caller's planes (strided 2-D copies; no host staging pass)
         ScopedTimer t(p, 1, s, &p->profile_ms[1]);
-        for (int u = 0; u < n_planes; ++u) {
-            if (!in_planes[u] || !out_planes[u]) return set_error(FDR_E_INVALID, "plane %d is NULL", u);
-            for (int y = 0; y < p->H; ++y)
-                memcpy(p->h_f32_in.p + u * HW + (size_t)y * p->W, reinterpret_cast<const char*>(in_planes[u]) + y * in_stride, rowb);
-        }
-        FDR_CUDA(cudaMemcpyAsync(p->d_in_f32.p, p->h_f32_in.p, HW * n_planes * sizeof(float), cudaMemcpyHostToDevice, s));
+        for (int u = 0; u < n_planes; ++u)
+            FDR_CUDA(cudaMemcpy2DAsync(p->d_in_f32.p + u * HW, rowb, in_planes[u], in_stride, rowb, p->H, cudaMemcpyHostToDevice, s));
         t.stop();
     }
     {
@@ -667,14 +664,8 @@ __attribute__((visibility("default"))) int fdr_restore_planes_host_f32(fdr_plan*
     }
     {
         ScopedTimer t(p, 3, s, &p->profile_ms[4]);
-        FDR_CUDA(cudaMemcpyAsync(p->h_f32_out.p, p->d_out_f32.p, HW * n_planes * sizeof(float), cudaMemcpyDeviceToHost, s));
-        t.stop();
-    }
-    {
-        ScopedTimer t(p, 0, s, &p->profile_ms[5]);
         for (int u = 0; u < n_planes; ++u)
-            for (int y = 0; y < p->H; ++y)
-                memcpy(reinterpret_cast<char*>(out_planes[u]) + y * out_stride, p->h_f32_out.p + u * HW + (size_t)y * p->W, rowb);
+            FDR_CUDA(cudaMemcpy2DAsync(out_planes[u], out_stride, p->d_out_f32.p + u * HW, rowb, rowb, p->H, cudaMemcpyDeviceToHost, s));
         t.stop();
     }
     return FDR_OK;
