@@ -1,0 +1,188 @@
+// col_tma.cu -- column pass (COL_WIENER) with TMA-staged tiles.
+//
+// Measured (profiles/time_passes.py): the plain column kernel is bound by the
+// LSU/L1 pipeline, not by HBM -- a warp that touches 32/CW rows x (CW*8) bytes costs one L1 tag
+// cycle per row segment, and those cycles are shared with the shared-memory traffic of the FFT
+// exchanges.  Here the strided tile (CW columns x N rows of a ROW-MAJOR plane) is moved by the
+// Tensor Memory Accelerator instead: cp.async.bulk.tensor 2-D boxes of CW x 256 elements land in
+// shared memory as a dense [row][CW] tile and leave the same way, so no LSU address divergence is
+// paid for global memory at all, and the row passes keep their fully coalesced row-major layout.
+//   load tile (TMA) -> registers -> FFT -> Wiener tile (TMA into the now idle exchange buffer) ->
+//   multiply, conj -> FFT -> registers -> shared -> store tile (TMA)
+// One 64 KB buffer per CTA serves as TMA landing zone, exchange buffer and TMA source; 2 CTAs/SM.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "passes_impl.cuh"
+
+namespace fdr {
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int x, int y, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(x), "r"(y),
+                 "r"(smem_u32(smem_src))
+                 : "memory");
+}
+
+template <int LOGN, int CW>
+__global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>::THREADS <= 512) ? 1024 / ColGeom<LOGN, CW>::THREADS : 1)
+    col_wiener_tma_kernel(const __grid_constant__ CUtensorMap tm_data, const __grid_constant__ CUtensorMap tm_w, const ColPassArgs a) {
+    using Gm = ColGeom<LOGN, CW>;
+    constexpr int N = Gm::N, E = Gm::E, T = Gm::T;
+    constexpr int BOX_ROWS = (N < 256) ? N : 256;
+    constexpr int NBOX = N / BOX_ROWS;
+    constexpr unsigned BOX_BYTES = BOX_ROWS * CW * sizeof(float2);
+    extern __shared__ __align__(128) float2 smem2[];
+    __shared__ __align__(8) unsigned long long bar;
+    float2* ex = smem2;
+    const int tid = threadIdx.x;
+    const int c = tid % CW, t = tid / CW;
+    const int x0 = blockIdx.x * CW * 2;   // tensor maps count 32-bit floats along x
+    const int y0 = blockIdx.y * N;        // pair p occupies tensor rows [p*N, (p+1)*N)
+    const int nbox_valid = (a.rows_valid + BOX_ROWS - 1) / BOX_ROWS;
+
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, nbox_valid * BOX_BYTES);
+        for (int b = 0; b < nbox_valid; ++b) tma_load_2d(ex + (size_t)b * BOX_ROWS * CW, &tm_data, x0, y0 + b * BOX_ROWS, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    float2 v[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int r = t + T * m;
+        v[m] = (r < a.rows_valid) ? ex[(size_t)r * CW + c] : make_float2(0.f, 0.f);
+    }
+    fft_forward<N, CW>(v, ex, a.tw, t, c);  // (its first exchange starts with a barrier: the tile is consumed)
+
+    __syncthreads();  // exchange buffer idle: bring in the Wiener tile
+    if (tid == 0) {
+        mbar_expect_tx(&bar, NBOX * BOX_BYTES);
+        for (int b = 0; b < NBOX; ++b) tma_load_2d(ex + (size_t)b * BOX_ROWS * CW, &tm_w, x0, b * BOX_ROWS, &bar);
+    }
+    mbar_wait(&bar, 1);
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const float2 y = cmul(v[m], ex[(size_t)(t + T * m) * CW + c]);
+        v[m] = make_float2(y.x, -y.y);
+    }
+    fft_forward<N, CW>(v, ex, a.tw, t, c);
+
+    __syncthreads();  // last exchange reads done
+#pragma unroll
+    for (int m = 0; m < E; ++m) ex[(size_t)(t + T * m) * CW + c] = v[m];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        for (int b = 0; b < NBOX; ++b) tma_store_2d(&tm_data, x0, y0 + b * BOX_ROWS, ex + (size_t)b * BOX_ROWS * CW);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// rows x cols complex plane(s), row-major: 2-D tensor of 32-bit floats [rows][2*cols], box = box_rows x (2*cw)
+static bool make_map(CUtensorMap* tm, const void* base, long long rows, int cols, int cw, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 8};
+    cuuint32_t box[2] = {(cuuint32_t)cw * 2, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool col_tma_applicable(const ColPassArgs& a) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* env = getenv("FDR_COL_TMA");
+        enabled = (env && atoi(env) == 0) ? 0 : 1;
+    }
+    if (!enabled || a.mode != COL_WIENER || a.conj || a.data_tiled || a.wiener_tiled) return false;
+    if (a.n < 256 || a.n > 4096 || (a.n & (a.n - 1))) return false;
+    const int cw = col_pass_tile_width(a.n);  // (the 1024 case falls back to this width when 4 does not divide the pitch)
+    if (a.pitch % cw != 0 || a.cplane != (long long)a.n * a.pitch) return false;
+    if ((reinterpret_cast<uintptr_t>(a.data) & 15) || (reinterpret_cast<uintptr_t>(a.wiener) & 15)) return false;
+    return get_encode() != nullptr;
+}
+
+template <int LOGN, int CW = default_col_cw(LOGN)> static cudaError_t launch_t(const ColPassArgs& a, cudaStream_t s) {
+    using Gm = ColGeom<LOGN, CW>;
+    constexpr int BOX_ROWS = (Gm::N < 256) ? Gm::N : 256;
+    CUtensorMap tm_data, tm_w;
+    if (!make_map(&tm_data, a.data, (long long)a.npairs * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
+    if (!make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
+    static unsigned long long configured = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(configured >> (dev & 63) & 1ULL)) {
+        cudaError_t e = cudaFuncSetAttribute(col_wiener_tma_kernel<LOGN, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+        if (e != cudaSuccess) return e;
+        configured |= 1ULL << (dev & 63);
+    }
+    dim3 grid(a.pitch / CW, a.npairs);
+    col_wiener_tma_kernel<LOGN, CW><<<grid, Gm::THREADS, Gm::SMEM, s>>>(tm_data, tm_w, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_col_wiener_tma(const ColPassArgs& a, cudaStream_t s) {
+    switch (a.n) {
+        case 256: return launch_t<8>(a, s);
+        case 512: return launch_t<9>(a, s);
+        case 1024: return (a.pitch % 4 == 0) ? launch_t<10, 4>(a, s) : launch_t<10>(a, s);  // 32 KB tiles, 4 CTAs/SM: measured best
+        case 2048: return launch_t<11>(a, s);
+        case 4096: return launch_t<12>(a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace fdr

@@ -88,6 +88,9 @@ cudaError_t get_twiddles(int n, const float2** out);
 // The Wiener factor it reads/writes is in digit-swapped row order: row 128*k1 + k2 holds frequency k1 + (n/128)*k2.
 bool col_split_applicable(const ColPassArgs& a);
 cudaError_t launch_col_split(const ColPassArgs& a, cudaStream_t s, int* launches);
+// COL_WIENER with TMA-staged tiles (col_tma.cu), 256 <= n <= 4096, row-major planes.
+bool col_tma_applicable(const ColPassArgs& a);
+cudaError_t launch_col_wiener_tma(const ColPassArgs& a, cudaStream_t s);
 // Tile width (columns per CTA) the column pass uses for length n.
 int col_pass_tile_width(int n);
 

@@ -303,14 +303,15 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
 }
 
 // ---------------------------------------------------------------------------------
-// Persistent column pass (COL_WIENER only; N*CW*8 B = 64 KB tiles, N <= 4096).
-// One CTA per SM walks a contiguous range of (column group, pair) work items, group-major:
-//   * the Wiener-factor tile of the group is fetched ONCE into shared memory (cp.async) and reused
-//     for every pair of the group -- Wf traffic drops from 8 B to 8/pairs B per pixel;
-//   * the next item's data tile is prefetched with cp.async into a staging buffer while the
-//     current tile is transformed in registers, so global-load latency is off the critical path;
-//   * results go straight from registers to global memory (fire-and-forget stores).
-// Shared memory: staging tile + Wiener tile + exchange buffer = 3 x 64 KB.
+// Pair-loop column pass (COL_WIENER only; N*CW*8 B = 64 KB tiles, 64 <= N <= 4096).
+// A CTA owns one column group at a time and walks all plane pairs of the launch for it:
+//   * the group's Wiener-factor tile is fetched ONCE into shared memory (cp.async) and reused for
+//     every pair -- Wf traffic drops from 8 B to 8/pairs B per pixel and leaves the load path;
+//   * the NEXT pair's data tile is loaded into a second register set while the current one is
+//     transformed, so global-load latency is hidden behind the two FFTs instead of serialised;
+//   * results go straight from registers to global memory.
+// Shared memory: exchange buffer + Wiener tile = 2 x 64 KB, one CTA per SM, <= 96 registers so row-pass
+// CTAs of other chunks (other streams) can still co-reside.
 // ---------------------------------------------------------------------------------
 template <int LOGN> struct ColPersistGeom {
     static constexpr int N = 1 << LOGN;
@@ -319,7 +320,7 @@ template <int LOGN> struct ColPersistGeom {
     static constexpr int CW = (N >= 256) ? (8192 / N) : 32;
     static constexpr int THREADS = T * CW;
     static constexpr size_t TILE = (size_t)N * CW * sizeof(float2);
-    static constexpr size_t SMEM = 3 * TILE;
+    static constexpr size_t SMEM = 2 * TILE;
     static constexpr int CHUNKS_PER_ROW = CW * 8 / 16;  // 16-byte cp.async chunks per tile row
 };
 
@@ -335,63 +336,57 @@ __global__ void __launch_bounds__(ColPersistGeom<LOGN>::THREADS, 1) col_wiener_p
     using Gm = ColPersistGeom<LOGN>;
     constexpr int N = Gm::N, E = Gm::E, T = Gm::T, CW = Gm::CW, CPR = Gm::CHUNKS_PER_ROW;
     extern __shared__ float2 smem2[];
-    float2* stage = smem2;                    // [N][CW] next tile
-    float2* wsm = smem2 + (size_t)N * CW;     // [N][CW] Wiener tile of the current group
-    float2* ex = smem2 + (size_t)2 * N * CW;  // exchange buffer
+    float2* ex = smem2;                     // exchange buffer
+    float2* wsm = smem2 + (size_t)N * CW;   // [N][CW] Wiener tile of the current group
     const int tid = threadIdx.x;
     const int c = tid % CW, t = tid / CW;
     const int ngroups = a.pitch / CW;
-    const long long items = (long long)ngroups * a.npairs;
-    const long long i0 = items * blockIdx.x / gridDim.x, i1 = items * (blockIdx.x + 1) / gridDim.x;
-    if (i0 >= i1) return;
     const long long stride = (long long)T * a.pitch;
 
-    auto issue_tile = [&](float2* dst, const float2* src_plane, int group, int rows) {
-        // rows x CW tile at columns [group*CW, +CW): CPR 16-byte chunks per row
-        const float2* src = src_plane + (long long)group * CW;
-        for (int q = tid; q < rows * CPR; q += Gm::THREADS) {
-            const int row = q / CPR, part = q % CPR;
-            cp_async16(dst + (size_t)row * CW + part * 2, src + (long long)row * a.pitch + part * 2);
-        }
+    auto load_tile = [&](float2 (&dst)[E], int g, int p) {
+        const float2* src = a.data + (long long)p * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
+#pragma unroll
+        for (int m = 0; m < E; ++m) dst[m] = (t + T * m < a.rows_valid) ? src[m * stride] : make_float2(0.f, 0.f);
     };
 
-    int cur_group = -1;
-    {
-        const int g = (int)(i0 / a.npairs), p = (int)(i0 % a.npairs);
-        issue_tile(stage, a.data + (long long)p * a.cplane, g, a.rows_valid);
-    }
-    for (long long i = i0; i < i1; ++i) {
-        const int g = (int)(i / a.npairs), p = (int)(i % a.npairs);
-        if (g != cur_group) {
-            issue_tile(wsm, a.wiener, g, N);
-            cur_group = g;
-        }
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncthreads();
-        float2 v[E];
-#pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const int r = t + T * m;
-            v[m] = (r < a.rows_valid) ? stage[(size_t)r * CW + c] : make_float2(0.f, 0.f);
-        }
-        __syncthreads();  // staging buffer free again
-        if (i + 1 < i1) {
-            const int g2 = (int)((i + 1) / a.npairs), p2 = (int)((i + 1) % a.npairs);
-            issue_tile(stage, a.data + (long long)p2 * a.cplane, g2, a.rows_valid);
+    float2 v[E], nx[E];
+    int g = blockIdx.x;
+    if (g >= ngroups) return;
+    load_tile(v, g, 0);
+    while (g < ngroups) {
+        // Wiener tile of this group -> shared memory
+        {
+            const float2* src = a.wiener + (long long)g * CW;
+            for (int q = tid; q < N * CPR; q += Gm::THREADS) {
+                const int row = q / CPR, part = q % CPR;
+                cp_async16(wsm + (size_t)row * CW + part * 2, src + (long long)row * a.pitch + part * 2);
+            }
             cp_async_commit();
         }
-        fft_forward<N, CW>(v, ex, a.tw, t, c);
+        const int g_next = g + gridDim.x;
+        for (int p = 0; p < a.npairs; ++p) {
+            // prefetch the next tile (next pair of this group, or pair 0 of this CTA's next group)
+            const bool more = (p + 1 < a.npairs) || (g_next < ngroups);
+            if (more) load_tile(nx, (p + 1 < a.npairs) ? g : g_next, (p + 1 < a.npairs) ? p + 1 : 0);
+            fft_forward<N, CW>(v, ex, a.tw, t, c);
+            if (p == 0) {
+                cp_async_wait_all();
+                __syncthreads();
+            }
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const float2 w = wsm[(size_t)(t + T * m) * CW + c];
-            const float2 y = cmul(v[m], w);
-            v[m] = make_float2(y.x, -y.y);
+            for (int m = 0; m < E; ++m) {
+                const float2 y = cmul(v[m], wsm[(size_t)(t + T * m) * CW + c]);
+                v[m] = make_float2(y.x, -y.y);
+            }
+            fft_forward<N, CW>(v, ex, a.tw, t, c);
+            float2* base = a.data + (long long)p * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
+#pragma unroll
+            for (int m = 0; m < E; ++m) base[m * stride] = v[m];
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = nx[m];
         }
-        fft_forward<N, CW>(v, ex, a.tw, t, c);
-        float2* base = a.data + (long long)p * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
-#pragma unroll
-        for (int m = 0; m < E; ++m) base[m * stride] = v[m];
+        __syncthreads();  // everyone is done with this group's Wiener tile
+        g = g_next;
     }
 }
 
@@ -405,9 +400,9 @@ template <int LOGN> cudaError_t launch_col_wiener_persistent(const ColPassArgs& 
         if (e != cudaSuccess) return e;
         configured |= 1ULL << (dev & 63);
     }
-    const long long items = (long long)(a.pitch / Gm::CW) * a.npairs;
+    const int ngroups = a.pitch / Gm::CW;
     int grid = num_sms;
-    if (grid > items) grid = (int)items;
+    if (grid > ngroups) grid = ngroups;
     col_wiener_persistent_kernel<LOGN><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
     return cudaGetLastError();
 }
