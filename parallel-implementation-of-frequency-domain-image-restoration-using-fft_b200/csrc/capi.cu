@@ -69,7 +69,6 @@ struct fdr_plan {
     cudaEvent_t lane_fork = nullptr, lane_join[4] = {};
     int last_lane = 0;
     int ws_units = 0;                 // per-lane workspace capacity in units
-    int tiled = 0;                    // column-tiled spectrum/Wiener layout inside the restore pipeline (FDR_TILED=1)
     const float2* tw_rows = nullptr;  // twiddles for length Cp (row passes)
     const float2* tw_cols = nullptr;  // twiddles for length Rp (column passes)
     // staging for the host entry points
@@ -222,9 +221,6 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r1.cout = spec_l;
         r1.cplane = (long long)p->plane_elems();
         r1.tw = p->tw_rows;
-        r1.tiled = p->tiled;
-        r1.tile_shift = ilog2(col_pass_tile_width(p->Rp));
-        r1.tile_rows_shift = ilog2(p->Rp);
         const double px_in = (double)p->H * p->W * (in.mode == ROW_IN_PAIR_U8 ? 1.0 : 4.0) * nu;
         const double P = (double)p->plane_elems();
         {
@@ -244,8 +240,6 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         c2.K = p->K;
         c2.tw = p->tw_cols;
         c2.persistent_sms = p->persistent_sms;
-        c2.data_tiled = p->tiled;
-        c2.wiener_tiled = p->tiled;
         {
             KernelTimer kt(p, s, 1, (8.0 * p->H * p->Cp + 16.0 * P) * np);
             if (p->col_split) {
@@ -274,9 +268,6 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         r3.minmax = mm_l;
         r3.local_units = nu;
         r3.tw = p->tw_rows;
-        r3.tiled = p->tiled;
-        r3.tile_shift = ilog2(col_pass_tile_width(p->Rp));
-        r3.tile_rows_shift = ilog2(p->Rp);
         {
             KernelTimer kt(p, s, 2, 8.0 * P * np + 4.0 * HW * nu);
             FDR_CUDA(launch_row_pass(r3, s));
@@ -343,7 +334,6 @@ int build_wiener_into(fdr_plan* p, DevBuf<float2>& dst, bool split) {
     if (split) {
         FDR_CUDA(launch_col_split(c, s, nullptr));
     } else {
-        c.wiener_tiled = p->tiled;
         FDR_CUDA(launch_col_pass(c, s));
     }
     FDR_CUDA(cudaStreamSynchronize(s));
@@ -461,9 +451,6 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
         }
         const char* ln = getenv("FDR_LANES");
         if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) p->lanes = atoi(ln);
-        const char* tl = getenv("FDR_TILED");
-        if (tl) p->tiled = atoi(tl) != 0;
-        if (p->Cp % col_pass_tile_width(p->Rp) != 0) p->tiled = 0;  // narrow images: plain row-major
         const char* fg = getenv("FDR_L2_FETCH");
         if (fg && atoi(fg) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
     }
@@ -590,18 +577,7 @@ __attribute__((visibility("default"))) int fdr_plan_get_wiener_host(const fdr_pl
                 memcpy(out + (size_t)(k1 + n1 * k2) * p->Cp, tmp.data() + (size_t)(128 * k1 + k2) * p->Cp, sizeof(float2) * p->Cp);
         return FDR_OK;
     }
-    if (!p->tiled) {
-        FDR_CUDA(cudaMemcpy(wf, p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
-        return FDR_OK;
-    }
-    // stored column-tiled [col/CW][row][col%CW]; hand back row-major (layout conversion only)
-    std::vector<float2> tmp(p->plane_elems());
-    FDR_CUDA(cudaMemcpy(tmp.data(), p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
-    const int cw = col_pass_tile_width(p->Rp);
-    float2* out = reinterpret_cast<float2*>(wf);
-    for (int g = 0; g < (p->Cp + cw - 1) / cw; ++g)
-        for (int r = 0; r < p->Rp; ++r)
-            for (int c = 0; c < cw && g * cw + c < p->Cp; ++c) out[(size_t)r * p->Cp + (size_t)g * cw + c] = tmp[((size_t)g * p->Rp + r) * cw + c];
+    FDR_CUDA(cudaMemcpy(wf, p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
     return FDR_OK;
 }
 
@@ -802,19 +778,16 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     r1.n = p->Cp; r1.nrows = p->H; r1.npairs = npairs; r1.in_mode = ROW_IN_PAIR_U8; r1.out_mode = ROW_OUT_COMPLEX;
     r1.in_u8 = p->d_in_u8.p; r1.channels = nu; r1.img_rows = p->H; r1.img_cols = p->W; r1.units_total = nu;
     r1.cout = p->spec.p; r1.cplane = (long long)p->plane_elems(); r1.tw = p->tw_rows;
-    r1.tiled = p->tiled; r1.tile_shift = ilog2(col_pass_tile_width(p->Rp)); r1.tile_rows_shift = ilog2(p->Rp);
     ColPassArgs c2{};
     c2.n = p->Rp; c2.pitch = p->Cp; c2.npairs = npairs; c2.rows_valid = p->H; c2.data = p->spec.p;
     c2.cplane = (long long)p->plane_elems(); c2.wiener = p->wiener.p; c2.K = p->K; c2.tw = p->tw_cols;
     c2.mode = variant == 2 ? COL_FFT : variant == 3 ? COL_COPY : COL_WIENER;
     c2.persistent_sms = (variant == 0) ? p->persistent_sms : 0;
-    c2.data_tiled = p->tiled; c2.wiener_tiled = p->tiled;
     RowPassArgs r3{};
     r3.n = p->Cp; r3.nrows = p->Rp; r3.npairs = npairs; r3.in_mode = ROW_IN_COMPLEX; r3.out_mode = ROW_OUT_REAL_PAIR;
     r3.cin = p->spec.p; r3.cplane = (long long)p->plane_elems(); r3.units_total = nu; r3.raw = p->raw.p;
     r3.raw_unit_stride = (long long)p->H * p->W; r3.raw_rows = p->H; r3.raw_cols = p->W; r3.minmax = p->mm.p; r3.local_units = nu;
     r3.tw = p->tw_rows;
-    r3.tiled = p->tiled; r3.tile_shift = ilog2(col_pass_tile_width(p->Rp)); r3.tile_rows_shift = ilog2(p->Rp);
     FDR_CUDA(launch_row_pass(r1, s));  // realistic data in the workspace
     FDR_CUDA(launch_minmax_reset(p->mm.p, nu, s));
     auto run = [&]() -> cudaError_t {
@@ -870,7 +843,6 @@ static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* 
     c.cplane = (long long)p->plane_elems();
     c.wiener = p->wiener.p;
     c.tw = p->tw_cols;
-    c.wiener_tiled = p->tiled;
     if (col_mode == COL_FILTER && p->col_split) {
         if (!p->wiener_nat.p) {
             // the row pass above wrote the image spectrum into spec; build the natural-order factor first
@@ -878,7 +850,6 @@ static int spectrum_host(fdr_plan* p, const float* plane, size_t stride, float* 
             FDR_CUDA(launch_row_pass(r, s));
         }
         c.wiener = p->wiener_nat.p;
-        c.wiener_tiled = 0;
     }
     FDR_CUDA(launch_col_pass(c, s));
     FDR_CUDA(cudaMemcpyAsync(out, p->spec.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost, s));

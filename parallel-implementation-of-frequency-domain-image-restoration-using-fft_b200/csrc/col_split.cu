@@ -43,8 +43,7 @@ static cudaError_t get_full_twiddles(int n, const float2** out) {
 }
 
 bool col_split_applicable(const ColPassArgs& a) {
-    return (a.n == 8192 || a.n == 16384) && (a.mode == COL_WIENER || a.mode == COL_MAKE_WIENER) && a.pitch % SPLIT_CWC == 0 &&
-           !a.data_tiled && !a.wiener_tiled && !a.conj;
+    return (a.n == 8192 || a.n == 16384) && (a.mode == COL_WIENER || a.mode == COL_MAKE_WIENER) && a.pitch % SPLIT_CWC == 0 && !a.conj;
 }
 
 template <int LOGN1> static cudaError_t launch_strided(const ColSplitArgs& s, cudaStream_t st) {

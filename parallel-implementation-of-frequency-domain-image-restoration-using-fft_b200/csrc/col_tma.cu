@@ -147,7 +147,7 @@ bool col_tma_applicable(const ColPassArgs& a) {
         const char* env = getenv("FDR_COL_TMA");
         enabled = (env && atoi(env) == 0) ? 0 : 1;
     }
-    if (!enabled || a.mode != COL_WIENER || a.conj || a.data_tiled || a.wiener_tiled) return false;
+    if (!enabled || a.mode != COL_WIENER || a.conj) return false;
     if (a.n < 256 || a.n > 4096 || (a.n & (a.n - 1))) return false;
     const int cw = col_pass_tile_width(a.n);  // (the 1024 case falls back to this width when 4 does not divide the pitch)
     if (a.pitch % cw != 0 || a.cplane != (long long)a.n * a.pitch) return false;

@@ -184,10 +184,11 @@ template <int N, int R, int NS> __device__ __forceinline__ void stage_butterflie
 
 // Scatter the stage outputs to shared memory and gather the next stage's inputs.
 // ex: this CTA's exchange buffer (N*CW float2); c = transform index in the tile.
-template <int N, int CW, int R, int NS> __device__ __forceinline__ void stage_exchange(float2* v, float2* ex, int t, int c) {
+// LEAD_SYNC = false when the caller guarantees nobody still reads `ex` (double-buffered exchanges).
+template <int N, int CW, int R, int NS, bool LEAD_SYNC = true> __device__ __forceinline__ void stage_exchange(float2* v, float2* ex, int t, int c) {
     constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T, NB = E / R;
     char* exb = reinterpret_cast<char*>(ex);
-    __syncthreads();
+    if constexpr (LEAD_SYNC) __syncthreads();
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int j = t + b * T;
@@ -202,15 +203,20 @@ template <int N, int CW, int R, int NS> __device__ __forceinline__ void stage_ex
     for (int m = 0; m < E; ++m) v[m] = *reinterpret_cast<const float2*>(exb + (r0 ^ (Swz<CW>::f(T * m) * CW * 8)));
 }
 
-template <int N, int CW, int NS> struct FftStages {
+// DB = true: `ex` holds TWO exchange buffers of N*CW float2 used alternately, which removes the
+// write-after-read barrier of every exchange (one __syncthreads per exchange instead of two).
+template <int N, int CW, int NS, bool DB = false, int XI = 0> struct FftStages {
     __device__ __forceinline__ static void run(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c) {
         constexpr int E = FftGeom<N>::E;
         constexpr int REM = N / NS;
         constexpr int R = (REM < E) ? REM : E;
         stage_butterflies<N, R, NS>(v, tw, t);
         if constexpr (NS * R < N) {
-            stage_exchange<N, CW, R, NS>(v, ex, t, c);
-            FftStages<N, CW, NS * R>::run(v, ex, tw, t, c);
+            if constexpr (DB)
+                stage_exchange<N, CW, R, NS, false>(v, ex + (size_t)(XI & 1) * N * CW, t, c);
+            else
+                stage_exchange<N, CW, R, NS, true>(v, ex, t, c);
+            FftStages<N, CW, NS * R, DB, XI + 1>::run(v, ex, tw, t, c);
         }
     }
 };
@@ -218,8 +224,8 @@ template <int N, int CW, int NS> struct FftStages {
 // Forward FFT of length N over the E points held by thread t (points t + T*m).
 // All T*CW threads of all transforms in the CTA must call this together when N > E
 // (it contains __syncthreads).
-template <int N, int CW> __device__ __forceinline__ void fft_forward(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c) {
-    if constexpr (N > 1) FftStages<N, CW, 1>::run(v, ex, tw, t, c);
+template <int N, int CW, bool DB = false> __device__ __forceinline__ void fft_forward(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c) {
+    if constexpr (N > 1) FftStages<N, CW, 1, DB>::run(v, ex, tw, t, c);
 }
 
 // Shared memory (bytes) one CTA needs for `ntransforms` interleaved transforms of length N.

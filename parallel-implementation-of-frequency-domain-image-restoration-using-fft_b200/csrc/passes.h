@@ -43,9 +43,6 @@ struct RowPassArgs {
     long long units_total;       // global unit count (a pair's second unit may not exist)
     // ---- complex input / output ----
     const float2* cin;           // pair p at cin + p*cplane, row r at + r*n
-    int tiled;                   // complex planes: 0 = row-major; 1 = column-tiled layout
-    int tile_shift;              //   [col >> k][row][col & (2^k - 1)], k = tile_shift,
-    int tile_rows_shift;         //   rows_padded = 1 << tile_rows_shift
     float2* cout;
     long long cplane;
     // ---- real-pair output (pass 3) ----
@@ -70,8 +67,6 @@ struct ColPassArgs {
     const float2* tw;     // twiddle table of length n
     int rows_valid;       // rows >= rows_valid are read as zero (pass 1 skipped them)
     float2* data;         // in place; pair p at data + p*cplane
-    int data_tiled;       // 1: data is in the column-tiled layout [col/CW][row][col%CW] (CW = this length's tile width)
-    int wiener_tiled;     // 1: the Wiener factor (read or written) is in that layout
     long long cplane;
     const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
     float2* wiener_out;   // COL_MAKE_WIENER

@@ -22,32 +22,14 @@ template <int LOGN> struct RowGeom {
     static constexpr int T = FftGeom<N>::T;
     static constexpr int RPC = (T >= 128) ? 1 : (128 / T);
     static constexpr int THREADS = T * RPC;
-    static constexpr size_t SMEM = fft_smem_bytes<N>(RPC);
+    static constexpr int MIN_BLOCKS = (THREADS == 128 && N >= 1024) ? 9 : 1;
+    // double-buffered exchange (one barrier per exchange) while two buffers of all rows fit 32 KB
+    static constexpr bool DB = false;  // measured slower on B200: the second buffer costs one resident CTA per SM
+    static constexpr size_t SMEM = fft_smem_bytes<N>(RPC) * (DB ? 2 : 1);
 };
 
-// Element (row, x) of a complex plane: row-major, or column-tiled [x >> k][row][x & (2^k-1)].
-__device__ __forceinline__ long long tiled_offset(const RowPassArgs& a, int row, int x) {
-    const int k = a.tile_shift;
-    return ((((long long)(x >> k) << a.tile_rows_shift) + row) << k) + (x & ((1 << k) - 1));
-}
-// Thread t of a row touches x = t + T*m.  When T is a multiple of the tile width the m-th element is
-// off0 + m*step; otherwise step = -1 and the caller evaluates tiled_offset per element.
-template <int N> __device__ __forceinline__ void complex_plane_addressing(const RowPassArgs& a, int row, int t, long long& off0, long long& step) {
-    constexpr int T = FftGeom<N>::T;
-    if (!a.tiled) {
-        off0 = (long long)row * N + t;
-        step = T;
-    } else if ((T >> a.tile_shift) << a.tile_shift == T && T >= (1 << a.tile_shift)) {
-        off0 = tiled_offset(a, row, t);
-        step = (long long)T << a.tile_rows_shift;
-    } else {
-        off0 = 0;
-        step = -1;
-    }
-}
-
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
-__global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const RowPassArgs a) {
+__global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLOCKS) row_pass_kernel(const RowPassArgs a) {
     using Gm = RowGeom<LOGN>;
     constexpr int N = Gm::N, E = Gm::E, T = Gm::T, RPC = Gm::RPC;
     extern __shared__ float2 smem2[];
@@ -57,20 +39,18 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
     const int row = blockIdx.x * RPC + rl;
     const int pair = blockIdx.y;
     const bool active = row < a.nrows;
-    float2* ex = smem2 + (size_t)rl * N;
+    float2* ex = smem2 + (size_t)rl * N * (Gm::DB ? 2 : 1);
 
     const long long u0 = 2LL * pair, u1 = u0 + 1;  // local units
     const bool has1 = (a.unit_base + u1) < a.units_total;
 
     float2 v[E];
     if constexpr (IN_MODE == ROW_IN_COMPLEX) {
-        long long off0, step;
-        complex_plane_addressing<N>(a, row, t, off0, step);
-        const float2* src = a.cin + (long long)pair * a.cplane + off0;
+        const float2* src = a.cin + (long long)pair * a.cplane + (long long)row * N + t;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             float2 z = make_float2(0.f, 0.f);
-            if (active) z = (step >= 0) ? src[m * step] : a.cin[(long long)pair * a.cplane + tiled_offset(a, row, t + T * m)];
+            if (active) z = src[T * m];
             if constexpr (CONJ) z.y = -z.y;
             v[m] = z;
         }
@@ -103,26 +83,49 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
         }
     } else {  // ROW_IN_PAIR_U8 : x * (float)(1/255.)  (serial.cpp:24-25 convertTo + /= 255.0)
         const long long g0 = a.unit_base + u0, g1 = has1 ? a.unit_base + u1 : g0;
-        const int C = a.channels;
-        const long long i0 = g0 / C, i1 = g1 / C;
-        const int c0 = (int)(g0 - i0 * C), c1 = (int)(g1 - i1 * C);
-        const uint8_t* p0 = a.in_u8 + ((i0 * a.img_rows + row) * (long long)a.img_cols) * C + c0;
-        const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row) * (long long)a.img_cols) * C + c1;
         const float inv255 = (float)(1.0 / 255.0);
         const float k1 = has1 ? inv255 : 0.f;
+        if (a.channels == 3) {
+            // BGR fast path: compile-time pixel stride, so every load is base + immediate
+            const long long i0 = g0 / 3, i1 = g1 / 3;
+            const int c0 = (int)(g0 - i0 * 3), c1 = (int)(g1 - i1 * 3);
+            const uint8_t* p0 = a.in_u8 + ((i0 * a.img_rows + row) * (long long)a.img_cols) * 3 + c0 + 3 * t;
+            const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row) * (long long)a.img_cols) * 3 + c1 + 3 * t;
+            if (active && a.img_cols == N) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) {
-            const int x = t + T * m;
-            float2 z = make_float2(0.f, 0.f);
-            if (active && x < a.img_cols) {
-                z.x = (float)__ldg(p0 + x * C) * inv255;
-                z.y = (float)__ldg(p1 + x * C) * k1;
+                for (int m = 0; m < E; ++m)
+                    v[m] = make_float2((float)__ldg(p0 + 3 * T * m) * inv255, (float)__ldg(p1 + 3 * T * m) * k1);
+            } else {
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    float2 z = make_float2(0.f, 0.f);
+                    if (active && t + T * m < a.img_cols) {
+                        z.x = (float)__ldg(p0 + 3 * T * m) * inv255;
+                        z.y = (float)__ldg(p1 + 3 * T * m) * k1;
+                    }
+                    v[m] = z;
+                }
             }
-            v[m] = z;
+        } else {
+            const int C = a.channels;
+            const long long i0 = g0 / C, i1 = g1 / C;
+            const int c0 = (int)(g0 - i0 * C), c1 = (int)(g1 - i1 * C);
+            const uint8_t* p0 = a.in_u8 + ((i0 * a.img_rows + row) * (long long)a.img_cols) * C + c0;
+            const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row) * (long long)a.img_cols) * C + c1;
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int x = t + T * m;
+                float2 z = make_float2(0.f, 0.f);
+                if (active && x < a.img_cols) {
+                    z.x = (float)__ldg(p0 + x * C) * inv255;
+                    z.y = (float)__ldg(p1 + x * C) * k1;
+                }
+                v[m] = z;
+            }
         }
     }
 
-    fft_forward<N, 1>(v, ex, a.tw, t, 0);
+    fft_forward<N, 1, Gm::DB>(v, ex, a.tw, t, 0);
 
     if constexpr (OUT_MODE == ROW_OUT_SCATTER) {
         if (active) {
@@ -137,17 +140,12 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
         }
     } else if constexpr (OUT_MODE == ROW_OUT_COMPLEX) {
         if (active) {
-            long long off0, step;
-            complex_plane_addressing<N>(a, row, t, off0, step);
-            float2* dst = a.cout + (long long)pair * a.cplane + off0;
+            float2* dst = a.cout + (long long)pair * a.cplane + (long long)row * N + t;
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 float2 z = v[m];
                 if constexpr (CONJ) z.y = -z.y;
-                if (step >= 0)
-                    dst[m * step] = z;
-                else
-                    a.cout[(long long)pair * a.cplane + tiled_offset(a, row, t + T * m)] = z;
+                dst[T * m] = z;
             }
         }
     } else {
@@ -166,11 +164,19 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS) row_pass_kernel(const 
             if (row < a.raw_rows) {
                 float* d0 = a.raw + u0 * a.raw_unit_stride + (long long)row * a.raw_cols + t;
                 float* d1 = a.raw + u1 * a.raw_unit_stride + (long long)row * a.raw_cols + t;
+                if (a.raw_cols == N && has1) {  // un-cropped width, full pair: no per-element predicates
 #pragma unroll
-                for (int m = 0; m < E; ++m) {
-                    if (t + T * m < a.raw_cols) {
+                    for (int m = 0; m < E; ++m) {
                         d0[T * m] = v[m].x;
-                        if (has1) d1[T * m] = v[m].y;
+                        d1[T * m] = v[m].y;
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < E; ++m) {
+                        if (t + T * m < a.raw_cols) {
+                            d0[T * m] = v[m].x;
+                            if (has1) d1[T * m] = v[m].y;
+                        }
                     }
                 }
             }
@@ -244,11 +250,9 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
     const int c = tid % CW, t = tid / CW;
     const int col = blockIdx.x * CW + c;
     const bool active = col < a.pitch;
-    // row-major: element (r, col) at r*pitch + col; column-tiled: (group*n + r)*CW + c, contiguous per CTA
-    const long long stride = a.data_tiled ? (long long)T * CW : (long long)T * a.pitch;
-    const long long first = a.data_tiled ? ((long long)blockIdx.x * N + t) * CW + c : (long long)t * a.pitch + col;
-    const long long wstride = a.wiener_tiled ? (long long)T * CW : (long long)T * a.pitch;
-    const long long wfirst = a.wiener_tiled ? ((long long)blockIdx.x * N + t) * CW + c : (long long)t * a.pitch + col;
+    const long long stride = (long long)T * a.pitch;
+    const long long first = (long long)t * a.pitch + col;
+    const long long wstride = stride, wfirst = first;
     float2* base = a.data + (long long)blockIdx.y * a.cplane + first;
 
     float2 v[E];
@@ -463,7 +467,7 @@ template <int LOGN, int CW> cudaError_t launch_col_pass_t(const ColPassArgs& a, 
             return a.conj ? launch_col_variant<LOGN, CW, COL_FFT, true>(a, s) : launch_col_variant<LOGN, CW, COL_FFT, false>(a, s);
         case COL_WIENER:
             if constexpr (LOGN >= 6 && LOGN <= 12) {
-                if (a.persistent_sms > 0 && !a.data_tiled && !a.wiener_tiled && a.pitch % ColPersistGeom<LOGN>::CW == 0)
+                if (a.persistent_sms > 0 && a.pitch % ColPersistGeom<LOGN>::CW == 0)
                     return launch_col_wiener_persistent<LOGN>(a, a.persistent_sms, s);
             }
             return launch_col_variant<LOGN, CW, COL_WIENER, false>(a, s);
