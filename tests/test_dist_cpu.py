@@ -49,6 +49,8 @@ class NumpyShard:
         self.npairs = (channels + 1) // 2
         self.path = os.path.join(tmp, "slab%d.bin" % rank)
         self.slab = np.memmap(self.path, dtype=np.complex128, mode="w+", shape=(self.npairs, self.Rp, self.Cl))
+        self.slab[:] = 0  # rows >= H are never written by anyone; zero BEFORE the handle exchange (a barrier),
+        self.slab.flush()  # never inside phase 1, where a faster peer may already be storing its rows here
         hp = np.zeros((self.Rp, self.Cp))
         hp[: psf.shape[0], : psf.shape[1]] = psf
         Hs = np.fft.fft2(hp)
@@ -65,7 +67,6 @@ class NumpyShard:
         return self.mm
 
     def phase1(self, rows_u8, stream=0):
-        self.slab[:] = 0  # rows >= H are never written by anyone
         x = rows_u8.astype(np.float64) / 255.0
         for p in range(self.npairs):
             a = x[:, :, 2 * p]
