@@ -164,6 +164,13 @@ int fdr_shard_set_psf_host(fdr_shard* shard, const float* psf, int psf_rows, int
 int fdr_shard_phase1_rows(fdr_shard* shard, const void* d_in_rows_u8, void* stream);
 int fdr_shard_phase2_cols(fdr_shard* shard, void* stream);
 int fdr_shard_phase3_rows(fdr_shard* shard, void* stream);
+/* The same phases restricted to plane pairs [pair_first, pair_first + pair_count) (a 3-channel image has
+ * 2 pairs: B+iG and R+i0).  Lets the caller pipeline the pairs on separate streams so that one pair's
+ * NVLink-bound row phase overlaps the other pair's HBM-bound column phase (fdr_dist.ShardedRestorer). */
+int fdr_shard_phase1_pairs(fdr_shard* shard, const void* d_in_rows_u8, int pair_first, int pair_count, void* stream);
+int fdr_shard_phase2_pairs(fdr_shard* shard, int pair_first, int pair_count, void* stream);
+int fdr_shard_phase3_pairs(fdr_shard* shard, int pair_first, int pair_count, void* stream);
+int fdr_shard_pair_count(const fdr_shard* shard, int* pairs);
 /* [channels][2] floats (min, max of this rank's part of every padded plane) to all-reduce in
  * place: column 0 with MIN, column 1 with MAX. */
 int fdr_shard_minmax_device(fdr_shard* shard, void** d_minmax_f32);

@@ -100,6 +100,7 @@ cudaError_t launch_col_split(const ColPassArgs& a, cudaStream_t st, int* launche
             s.data = a.data;
             s.cplane = a.cplane;
             s.npairs = a.npairs;
+            s.pair_base = a.pair_base;
             s.wiener = a.wiener;
             s.wiener_out = a.wiener_out;
             s.K = a.K;

@@ -28,7 +28,7 @@ struct ColSplitArgs {
     int n;               // column length
     int pitch;           // elements per row
     int col0, ncols;     // panel [col0, col0 + ncols), multiples of 16
-    int npairs;
+    int npairs, pair_base;
     int rows_valid;      // kernel A: rows >= rows_valid read as zero
     int twiddle;         // strided kernel: multiply by W_N^{n2*k1} after the transform
     int mode;            // block kernel: COL_WIENER or COL_MAKE_WIENER
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__((1 << LOGN1) / 16 * SPLIT_CWC * SPLIT_NJ) col_
     const int c = cc % SPLIT_CWC, j = cc / SPLIT_CWC;
     const int n2 = blockIdx.y * SPLIT_NJ + j;
     const int col = a.col0 + blockIdx.x * SPLIT_CWC + c;
-    float2* base = a.data + (long long)blockIdx.z * a.cplane + (long long)n2 * a.pitch + col;
+    float2* base = a.data + (long long)(blockIdx.z + a.pair_base) * a.cplane + (long long)n2 * a.pitch + col;
     const long long rstride = (long long)SPLIT_N2 * a.pitch;  // rows n2 + 128*k
     float2 v[E];
 #pragma unroll
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(SPLIT_N2 / 16 * SPLIT_CWC * SPLIT_NJ, 4) col_s
     const int col = a.col0 + blockIdx.x * SPLIT_CWC + c;
     const long long first = ((long long)k1 * N2 + t) * a.pitch + col;
     const long long rstride = (long long)T * a.pitch;
-    float2* base = a.data + (long long)blockIdx.z * a.cplane + first;
+    float2* base = a.data + (long long)(blockIdx.z + a.pair_base) * a.cplane + first;
     float2 v[E];
 #pragma unroll
     for (int m = 0; m < E; ++m) v[m] = base[m * rstride];

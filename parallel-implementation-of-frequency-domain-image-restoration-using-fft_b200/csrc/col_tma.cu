@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
     const int tid = threadIdx.x;
     const int c = tid % CW, t = tid / CW;
     const int x0 = blockIdx.x * CW * 2;   // tensor maps count 32-bit floats along x
-    const int y0 = blockIdx.y * N;        // pair p occupies tensor rows [p*N, (p+1)*N)
+    const int y0 = (blockIdx.y + a.pair_base) * N;  // pair p occupies tensor rows [p*N, (p+1)*N)
     const int nbox_valid = (a.rows_valid + BOX_ROWS - 1) / BOX_ROWS;
 
     if (tid == 0) {
@@ -159,7 +159,7 @@ template <int LOGN, int CW = default_col_cw(LOGN)> static cudaError_t launch_t(c
     using Gm = ColGeom<LOGN, CW>;
     constexpr int BOX_ROWS = (Gm::N < 256) ? Gm::N : 256;
     CUtensorMap tm_data, tm_w;
-    if (!make_map(&tm_data, a.data, (long long)a.npairs * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
+    if (!make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
     if (!make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
     static unsigned long long configured = 0;
     int dev = 0;

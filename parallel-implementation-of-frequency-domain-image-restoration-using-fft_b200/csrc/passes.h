@@ -29,6 +29,7 @@ struct RowPassArgs {
     int n;               // transform length (padded columns), power of two
     int nrows;           // rows transformed per pair (grid.x covers them)
     int npairs;          // grid.y
+    int pair_base;       // first pair of this launch (pairs pair_base .. pair_base+npairs-1 of the workspace)
     int in_mode, out_mode;
     int conj;            // complex->complex only: conjugate on load and on store (inverse = conj FFT conj)
     const float2* tw;    // twiddle table of length n (get_twiddles)
@@ -62,6 +63,7 @@ struct ColPassArgs {
     int n;                // transform length (padded rows), power of two
     int pitch;            // elements per row (padded columns)
     int npairs;           // grid.y
+    int pair_base;        // first pair of this launch
     int mode;             // ColMode
     int conj;             // COL_FFT only: inverse transform
     const float2* tw;     // twiddle table of length n

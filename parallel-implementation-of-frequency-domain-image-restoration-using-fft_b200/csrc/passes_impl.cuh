@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLO
     const int rl = (RPC > 1) ? (tid / T) : 0;
     const int t = (RPC > 1) ? (tid % T) : tid;
     const int row = blockIdx.x * RPC + rl;
-    const int pair = blockIdx.y;
+    const int pair = blockIdx.y + a.pair_base;
     const bool active = row < a.nrows;
     float2* ex = smem2 + (size_t)rl * N * (Gm::DB ? 2 : 1);
 
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
     const long long stride = (long long)T * a.pitch;
     const long long first = (long long)t * a.pitch + col;
     const long long wstride = stride, wfirst = first;
-    float2* base = a.data + (long long)blockIdx.y * a.cplane + first;
+    float2* base = a.data + (long long)(blockIdx.y + a.pair_base) * a.cplane + first;
 
     float2 v[E];
 #pragma unroll
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(ColPersistGeom<LOGN>::THREADS, 1) col_wiener_p
     const long long stride = (long long)T * a.pitch;
 
     auto load_tile = [&](float2 (&dst)[E], int g, int p) {
-        const float2* src = a.data + (long long)p * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
+        const float2* src = a.data + (long long)(p + a.pair_base) * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
 #pragma unroll
         for (int m = 0; m < E; ++m) dst[m] = (t + T * m < a.rows_valid) ? src[m * stride] : make_float2(0.f, 0.f);
     };
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(ColPersistGeom<LOGN>::THREADS, 1) col_wiener_p
                 v[m] = make_float2(y.x, -y.y);
             }
             fft_forward<N, CW>(v, ex, a.tw, t, c);
-            float2* base = a.data + (long long)p * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
+            float2* base = a.data + (long long)(p + a.pair_base) * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
 #pragma unroll
             for (int m = 0; m < E; ++m) base[m * stride] = v[m];
 #pragma unroll

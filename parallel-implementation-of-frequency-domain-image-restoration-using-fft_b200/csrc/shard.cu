@@ -266,20 +266,38 @@ FDR_API int fdr_shard_set_psf_host(fdr_shard* s, const float* psf, int psf_rows,
 
 // phase 1: rows forward + scatter to the owners of the columns.  d_in_rows: this rank's rows of
 // the image, interleaved u8 [rows_local][W][C].
+static int check_pairs(const fdr_shard* s, int pair_first, int pair_count) {
+    if (pair_first < 0 || pair_count < 1 || pair_first + pair_count > s->npairs)
+        return set_error(FDR_E_INVALID, "pair range [%d, +%d) outside 0..%d", pair_first, pair_count, s->npairs);
+    return FDR_OK;
+}
+
 FDR_API int fdr_shard_phase1_rows(fdr_shard* s, const void* d_in_rows_u8, void* stream) {
     if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    return fdr_shard_phase1_pairs(s, d_in_rows_u8, 0, s->npairs, stream);
+}
+
+FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int pair_first, int pair_count, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
     if (!s->have_peers || !s->have_wiener) return set_error(FDR_E_STATE, "set peers and PSF before phase 1");
+    FDR_TRY(check_pairs(s, pair_first, pair_count));
     FDR_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = pick(s, stream);
-    s->launches = 0;
-    FDR_CUDA(launch_minmax_reset(s->mm.p, s->C, st));
-    s->launches += 1;
+    if (pair_first == 0) s->launches = 0;
+    {   // extrema of the planes these pairs carry
+        const int u0 = 2 * pair_first;
+        int nu = 2 * pair_count;
+        if (u0 + nu > s->C) nu = s->C - u0;
+        FDR_CUDA(launch_minmax_reset(s->mm.p + 2 * u0, nu, st));
+        s->launches += 1;
+    }
     if (s->rows_local == 0) return FDR_OK;  // slab entirely inside the zero padding
     if (!d_in_rows_u8) return set_error(FDR_E_INVALID, "input rows are NULL");
     RowPassArgs r{};
     r.n = s->Cp;
     r.nrows = s->rows_local;
-    r.npairs = s->npairs;
+    r.npairs = pair_count;
+    r.pair_base = pair_first;
     r.in_mode = ROW_IN_PAIR_U8;
     r.out_mode = ROW_OUT_SCATTER;
     r.in_u8 = static_cast<const uint8_t*>(d_in_rows_u8);
@@ -301,11 +319,18 @@ FDR_API int fdr_shard_phase1_rows(fdr_shard* s, const void* d_in_rows_u8, void* 
 // phase 2: columns of the local slab, in place (FFT, Wiener factor, inverse FFT).
 FDR_API int fdr_shard_phase2_cols(fdr_shard* s, void* stream) {
     if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    return fdr_shard_phase2_pairs(s, 0, s->npairs, stream);
+}
+
+FDR_API int fdr_shard_phase2_pairs(fdr_shard* s, int pair_first, int pair_count, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    FDR_TRY(check_pairs(s, pair_first, pair_count));
     FDR_CUDA(cudaSetDevice(s->device));
     ColPassArgs c{};
     c.n = s->Rp;
     c.pitch = s->Cl;
-    c.npairs = s->npairs;
+    c.npairs = pair_count;
+    c.pair_base = pair_first;
     c.mode = COL_WIENER;
     c.rows_valid = s->H;
     c.data = s->slab.p;
@@ -328,12 +353,19 @@ FDR_API int fdr_shard_phase2_cols(fdr_shard* s, void* stream) {
 // phase 3: gather the local padded rows from every slab, inverse rows, min/max of the local part.
 FDR_API int fdr_shard_phase3_rows(fdr_shard* s, void* stream) {
     if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    return fdr_shard_phase3_pairs(s, 0, s->npairs, stream);
+}
+
+FDR_API int fdr_shard_phase3_pairs(fdr_shard* s, int pair_first, int pair_count, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    FDR_TRY(check_pairs(s, pair_first, pair_count));
     FDR_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = pick(s, stream);
     RowPassArgs r{};
     r.n = s->Cp;
     r.nrows = s->Rl;
-    r.npairs = s->npairs;
+    r.npairs = pair_count;
+    r.pair_base = pair_first;
     r.in_mode = ROW_IN_GATHER;
     r.out_mode = ROW_OUT_REAL_PAIR;
     r.unit_base = 0;
@@ -350,7 +382,12 @@ FDR_API int fdr_shard_phase3_rows(fdr_shard* s, void* stream) {
     r.peer_plane = (long long)s->Rp * s->Cl;
     r.row0 = s->row0;
     FDR_CUDA(launch_row_pass(r, st));
-    FDR_CUDA(launch_minmax_decode(s->mm.p, s->mmf.p, s->C, st));
+    {
+        const int u0 = 2 * pair_first;
+        int nu = 2 * pair_count;
+        if (u0 + nu > s->C) nu = s->C - u0;
+        FDR_CUDA(launch_minmax_decode(s->mm.p + 2 * u0, s->mmf.p + 2 * u0, nu, st));
+    }
     s->launches += 2;
     return FDR_OK;
 }
@@ -375,6 +412,12 @@ FDR_API int fdr_shard_phase4_pack(fdr_shard* s, void* d_out_rows_u8, void* strea
     FDR_CUDA(launch_pack_u8(s->raw.p, (long long)s->rows_local * s->W, s->ss.p, static_cast<uint8_t*>(d_out_rows_u8), 1, s->C,
                             s->rows_local, s->W, st));
     s->launches += 1;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_pair_count(const fdr_shard* s, int* pairs) {
+    if (!s || !pairs) return set_error(FDR_E_INVALID, "bad arguments");
+    *pairs = s->npairs;
     return FDR_OK;
 }
 

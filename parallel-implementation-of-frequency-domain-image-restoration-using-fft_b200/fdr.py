@@ -87,6 +87,10 @@ def lib():
             "fdr_shard_phase1_rows": [vp, vp, vp],
             "fdr_shard_phase2_cols": [vp, vp],
             "fdr_shard_phase3_rows": [vp, vp],
+            "fdr_shard_phase1_pairs": [vp, vp, i, i, vp],
+            "fdr_shard_phase2_pairs": [vp, i, i, vp],
+            "fdr_shard_phase3_pairs": [vp, i, i, vp],
+            "fdr_shard_pair_count": [vp, C.POINTER(i)],
             "fdr_shard_minmax_device": [vp, pp],
             "fdr_shard_phase4_pack": [vp, vp, vp],
             "fdr_shard_last_launch_count": [vp, C.POINTER(ll)],
@@ -314,14 +318,29 @@ class Shard:
         psf = _f32(psf)
         _check(lib().fdr_shard_set_psf_host(self.h, _p(psf), psf.shape[0], psf.shape[1], K))
 
-    def phase1(self, d_in_rows, stream=0):
-        _check(lib().fdr_shard_phase1_rows(self.h, d_in_rows, stream))
+    @property
+    def npairs(self):
+        n = C.c_int(0)
+        _check(lib().fdr_shard_pair_count(self.h, C.byref(n)))
+        return n.value
 
-    def phase2(self, stream=0):
-        _check(lib().fdr_shard_phase2_cols(self.h, stream))
+    def phase1(self, d_in_rows, stream=0, pair=None):
+        if pair is None:
+            _check(lib().fdr_shard_phase1_rows(self.h, d_in_rows, stream))
+        else:
+            _check(lib().fdr_shard_phase1_pairs(self.h, d_in_rows, pair, 1, stream))
 
-    def phase3(self, stream=0):
-        _check(lib().fdr_shard_phase3_rows(self.h, stream))
+    def phase2(self, stream=0, pair=None):
+        if pair is None:
+            _check(lib().fdr_shard_phase2_cols(self.h, stream))
+        else:
+            _check(lib().fdr_shard_phase2_pairs(self.h, pair, 1, stream))
+
+    def phase3(self, stream=0, pair=None):
+        if pair is None:
+            _check(lib().fdr_shard_phase3_rows(self.h, stream))
+        else:
+            _check(lib().fdr_shard_phase3_pairs(self.h, pair, 1, stream))
 
     def minmax_ptr(self):
         ptr = C.c_void_p()

@@ -68,14 +68,50 @@ class ShardedRestorer:
         backend.set_peers_from_handles(handles)
         self._mm = backend.minmax_tensor(device)      # [channels][2] view, all-reduced in place
         self._flag = torch.zeros(1, dtype=torch.float32, device=self._mm.device)
+        self._side = None                             # side streams + flags of the pair pipeline
 
-    def barrier(self):
+    def barrier(self, flag=None):
         """Stream-ordered cross-rank barrier: a 1-element all-reduce on the current stream."""
         if self.world > 1:
-            dist.all_reduce(self._flag, group=self.group)
+            dist.all_reduce(self._flag if flag is None else flag, group=self.group)
 
-    def restore_rows(self, d_in_rows, d_out_rows, stream=0):
+    def _restore_rows_pair_pipeline(self, d_in_rows, d_out_rows, stream):
+        """Two plane pairs on two side streams: pair 1's NVLink-bound row phase overlaps pair 0's
+        HBM-bound column phase (and so on).  Every rank issues the collectives in the same order."""
         b = self.b
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            dev = self._mm.device
+            self._side = [(torch.cuda.Stream(device=dev), torch.zeros(1, dtype=torch.float32, device=dev)) for _ in range(2)]
+        for st, _ in self._side:
+            st.wait_stream(main)
+        for phase in (1, 2, 3):
+            for pair, (st, flag) in enumerate(self._side):
+                with torch.cuda.stream(st):
+                    if phase == 1:
+                        b.phase1(d_in_rows, st.cuda_stream, pair=pair)
+                    elif phase == 2:
+                        b.phase2(st.cuda_stream, pair=pair)
+                    else:
+                        b.phase3(st.cuda_stream, pair=pair)
+                    if phase < 3:
+                        self.barrier(flag)
+        for st, _ in self._side:
+            main.wait_stream(st)
+
+    def restore_rows(self, d_in_rows, d_out_rows, stream=0, pipeline_pairs=True):
+        b = self.b
+        if (pipeline_pairs and self.world > 1 and getattr(b, "supports_pair_pipeline", False) and b.npairs == 2
+                and torch.cuda.current_stream().cuda_stream == stream):
+            self._restore_rows_pair_pipeline(d_in_rows, d_out_rows, stream)
+            mn = self._mm[:, 0].contiguous()
+            mx = self._mm[:, 1].contiguous()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            self._mm[:, 0].copy_(mn)
+            self._mm[:, 1].copy_(mx)
+            b.phase4(d_out_rows, stream)
+            return
         b.phase1(d_in_rows, stream)
         self.barrier()                      # every slab has received all its columns
         b.phase2(stream)
@@ -95,4 +131,5 @@ def cuda_shard_backend(fdr, rows, cols, channels, rank, world, device_index):
     """fdr.Shard plus the two hooks ShardedRestorer needs."""
     sh = fdr.Shard(rows, cols, channels, rank, world, device_index)
     sh.minmax_tensor = lambda device: device_tensor(sh.minmax_ptr(), (channels, 2), device or torch.device("cuda", device_index))
+    sh.supports_pair_pipeline = True
     return sh

@@ -70,6 +70,52 @@ def test_sharded_equals_single_gpu_and_oracle(gpu, oracle, H, W, world):
     assert worse == 0 and (exact + off1) / got.size >= 0.999
 
 
+def test_sharded_per_pair_phases(gpu, oracle):
+    """fdr_shard_phase*_pairs: running the two plane pairs separately (as the pipelined driver does)
+    gives the same bytes as the all-pairs phases."""
+    torch = pytest.importorskip("torch")
+    H, W, world = 192, 256, 2
+    img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 1, H, W), (1, 2, 0)))
+    want, _ = run_emulated(gpu, torch, img, world, 9, 30.0)
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(img).to(dev)
+    d_out = torch.zeros_like(d_in)
+    dist_mod = _load("fdr_dist", PKG + "/fdr_dist.py")
+    shards = [gpu.Shard(H, W, 3, g, world, 0) for g in range(world)]
+    try:
+        slabs = [s.local_slab()[0] for s in shards]
+        for s in shards:
+            assert s.npairs == 2
+            s.set_peers(slabs)
+            s.set_psf_motion(9, 30.0, K)
+        st = torch.cuda.Stream(device=dev)
+        rb = W * 3
+        for ph in (1, 2, 3):
+            for pair in (1, 0):  # order between pairs must not matter
+                for s in shards:
+                    if ph == 1:
+                        s.phase1(d_in.data_ptr() + s.first_row * rb, st.cuda_stream, pair=pair)
+                    elif ph == 2:
+                        s.phase2(st.cuda_stream, pair=pair)
+                    else:
+                        s.phase3(st.cuda_stream, pair=pair)
+                torch.cuda.synchronize()
+        mms = [dist_mod.device_tensor(s.minmax_ptr(), (3, 2), dev) for s in shards]
+        allmm = torch.stack(mms)
+        gmin, gmax = allmm[:, :, 0].min(0).values, allmm[:, :, 1].max(0).values
+        for t in mms:
+            t[:, 0] = gmin
+            t[:, 1] = gmax
+        torch.cuda.synchronize()
+        for s in shards:
+            s.phase4(d_out.data_ptr() + s.first_row * rb, st.cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), want)
+    finally:
+        for s in shards:
+            s.close()
+
+
 def test_sharded_4096_world8(gpu, oracle):
     """A BASELINE-sized plane through the sharded kernels (column slabs of 512 columns)."""
     torch = pytest.importorskip("torch")
