@@ -38,7 +38,10 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise FdrError("CUDA library not built: %s (run `make -C %s`)" % (LIB_PATH, HERE))
+            try:  # the in-tree library normally travels with the snapshot; build it if it did not
+                build()
+            except Exception as e:
+                raise FdrError("CUDA library not built and building failed: %s (run `make -C %s`): %s" % (LIB_PATH, HERE, e))
         L = C.CDLL(LIB_PATH)
         L.fdr_last_error.restype = C.c_char_p
         vp, i, f, d, sz, ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_longlong
