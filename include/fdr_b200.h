@@ -54,6 +54,14 @@ int fdr_plan_create(fdr_plan** plan, int rows, int cols, int channels, int max_i
 int fdr_plan_destroy(fdr_plan* plan);
 /* Padded sizes chosen by the plan (nextPowerOfTwo, utils.hpp:27-31). */
 int fdr_plan_padded_size(const fdr_plan* plan, int* padded_rows, int* padded_cols);
+/* 8-bit image outputs pass through the reference drivers' post stage (gpu.cpp:123-134 = serial.cpp:43-54):
+ * BGR -> Lab, L scaled by mean(L_original)/(mean(L_restored)+1e-6) and clamped (applyWhiteBalance,
+ * utils.hpp:55-71), Lab -> BGR, convertTo(CV_8U, 255).  Off by default (direct x255 pack). */
+int fdr_plan_set_white_balance(fdr_plan* plan, int enabled);
+/* The post stage alone, for callers that hold normalised planes (what fft_gpu::wienerDeblur_RGB_* returns):
+ * restored and original planes in B, G, R order, fp32 in [0,1], contiguous rows x cols -> 8-bit BGR image. */
+int fdr_white_balance_pack_host(const float* const* restored_planes, const float* const* original_planes, int rows, int cols,
+                                uint8_t* out_bgr);
 /* Images per internal chunk (0 = automatic).  Tuning knob; results do not depend on it. */
 int fdr_plan_set_chunk_images(fdr_plan* plan, int images);
 

@@ -59,6 +59,8 @@ struct fdr_plan {
     DevBuf<unsigned int> mm;      // chunk units x 2
     DevBuf<float2> ss;            // chunk units
     DevBuf<float> mmf;            // chunk units x 2
+    DevBuf<double> wb_sums;       // chunk images x 2 (Lab white balance)
+    int white_balance = 0;        // 8-bit outputs go through the Lab white-balance stage (gpu.cpp:123-134)
     DevBuf<float2> wiener;        // Rp x Cp (digit-swapped row order when col_split is set)
     DevBuf<float2> wiener_nat;    // natural-order copy, built lazily for the parity-gate API of long-column plans
     bool col_split = false;       // long columns: four-step column pass (col_split.cuh)
@@ -157,6 +159,7 @@ int ensure_workspace(fdr_plan* p, int chunk_units) {
     FDR_TRY(p->mm.ensure(L * chunk_units * 2));
     FDR_TRY(p->ss.ensure(L * chunk_units));
     FDR_TRY(p->mmf.ensure(L * chunk_units * 2));
+    FDR_TRY(p->wb_sums.ensure(L * chunk_units * 2));
     p->ws_units = chunk_units;
     if (p->lanes > 1 && !p->lane_fork) {
         FDR_CUDA(cudaEventCreateWithFlags(&p->lane_fork, cudaEventDisableTiming));
@@ -275,7 +278,14 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
 
         FDR_CUDA(launch_minmax_finalize(mm_l, ss_l, mmf_l, nu, s));
         p->launches += 5;
-        if (out_u8) {
+        if (out_u8 && p->white_balance && C == 3) {
+            KernelTimer kt(p, s, 3, (2 * 12.0 + 3.0 + (in.mode == ROW_IN_PAIR_U8 ? 3.0 : 12.0)) * HW * (nu / 3));
+            const uint8_t* o8 = in.mode == ROW_IN_PAIR_U8 ? in.u8 + base * HW : nullptr;
+            const float* of = in.mode == ROW_IN_PAIR_U8 ? nullptr : in.f32 + base * in.unit_stride;
+            FDR_CUDA(launch_white_balance_pack_u8(raw_l, HW, ss_l, o8, of, in.unit_stride, p->wb_sums.p + (size_t)lane * p->ws_units * 2,
+                                                  out_u8 + base * HW, nu / 3, p->H, p->W, s));
+            p->launches += 3;
+        } else if (out_u8) {
             KernelTimer kt(p, s, 3, 5.0 * HW * nu);
             FDR_CUDA(launch_pack_u8(raw_l, HW, ss_l, out_u8 + base * HW, nu / C, C, p->H, p->W, s));
             p->launches += 1;
@@ -475,6 +485,7 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
     p->mm.release();
     p->ss.release();
     p->mmf.release();
+    p->wb_sums.release();
     p->wiener.release();
     p->wiener_nat.release();
     p->psf.release();
@@ -514,6 +525,13 @@ __attribute__((visibility("default"))) int fdr_plan_padded_size(const fdr_plan* 
     if (!p) return set_error(FDR_E_INVALID, "plan is NULL");
     if (pr) *pr = p->Rp;
     if (pc) *pc = p->Cp;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_set_white_balance(fdr_plan* p, int enabled) {
+    if (!p) return set_error(FDR_E_INVALID, "plan is NULL");
+    if (enabled && p->C != 3) return set_error(FDR_E_INVALID, "white balance needs 3-channel (BGR) images");
+    p->white_balance = enabled != 0;
     return FDR_OK;
 }
 
@@ -962,6 +980,44 @@ __attribute__((visibility("default"))) int fdr_dft_naive_host(float* data, int n
 }
 
 __attribute__((visibility("default"))) int fdr_transform_rows_host(float* data, int rows, int n, int inverse) { return transform_host(data, rows, n, inverse, true, false); }
+
+// The drivers' post stage alone (gpu.cpp:123-134): restored planes + original planes (B, G, R; f32 in
+// [0,1]; rows x cols, contiguous) -> white-balanced 8-bit BGR image.  Runs on the current device.
+__attribute__((visibility("default"))) int fdr_white_balance_pack_host(const float* const* restored_planes, const float* const* original_planes, int rows,
+                                                                 int cols, uint8_t* out_bgr) {
+    if (!restored_planes || !original_planes || !out_bgr || rows < 1 || cols < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    const size_t HW = (size_t)rows * cols;
+    float *d_r = nullptr, *d_o = nullptr;
+    double* d_s = nullptr;
+    float2* d_ss = nullptr;
+    uint8_t* d_out = nullptr;
+    int rc = FDR_OK;
+    cudaError_t e = cudaMalloc(&d_r, 3 * HW * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_o, 3 * HW * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ss, 3 * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, 3 * HW);
+    const float2 ident[3] = {{1.f, 0.f}, {1.f, 0.f}, {1.f, 0.f}};
+    if (e == cudaSuccess) e = cudaMemcpy(d_ss, ident, sizeof(ident), cudaMemcpyHostToDevice);
+    for (int c = 0; c < 3 && e == cudaSuccess; ++c) {
+        if (!restored_planes[c] || !original_planes[c]) {
+            rc = set_error(FDR_E_INVALID, "plane %d is NULL", c);
+            break;
+        }
+        e = cudaMemcpy(d_r + c * HW, restored_planes[c], HW * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_o + c * HW, original_planes[c], HW * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (rc == FDR_OK && e == cudaSuccess) e = launch_white_balance_pack_u8(d_r, (long long)HW, d_ss, nullptr, d_o, (long long)HW, d_s, d_out, 1, rows, cols, 0);
+    if (rc == FDR_OK && e == cudaSuccess) e = cudaMemcpy(out_bgr, d_out, 3 * HW, cudaMemcpyDeviceToHost);
+    cudaFree(d_r);
+    cudaFree(d_o);
+    cudaFree(d_s);
+    cudaFree(d_ss);
+    cudaFree(d_out);
+    if (rc != FDR_OK) return rc;
+    if (e != cudaSuccess) return set_error(FDR_E_CUDA, "white balance: %s", cudaGetErrorString(e));
+    return FDR_OK;
+}
 
 // Plain copies for harnesses that hold raw device pointers (kind: 0 = H2D, 1 = D2H, 2 = D2D).
 __attribute__((visibility("default"))) int fdr_memcpy(void* dst, const void* src, size_t bytes, int kind) {

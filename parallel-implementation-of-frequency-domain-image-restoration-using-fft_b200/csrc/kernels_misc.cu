@@ -195,6 +195,133 @@ cudaError_t launch_pack_u8(const float* raw, long long raw_unit_stride, const fl
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------
+// Pass 4c: the post stage of every reference driver (gpu.cpp:123-134, serial.cpp:43-54):
+//   merged BGR -> Lab, L *= mean(L_original)/(mean(L_restored)+1e-6), clamp L to [0,100]
+//   (applyWhiteBalance, utils.hpp:55-71), Lab -> BGR, convertTo(CV_8U, 255).
+// Lab follows OpenCV's definition for float images (sRGB gamma, D65 white point
+// {0.950456, 1, 1.088754}, L in [0,100]) evaluated with the closed-form expressions; OpenCV itself
+// interpolates a 33^3 fixed-point table for float input, so the two agree to within +-1 LSB of the
+// 8-bit result (tests/test_gpu_whitebalance.py), not bit for bit.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float srgb_to_linear(float c) {
+    return c <= 0.04045f ? c * (1.0f / 12.92f) : powf((c + 0.055f) * (1.0f / 1.055f), 2.4f);
+}
+__device__ __forceinline__ float linear_to_srgb(float c) {
+    c = fminf(fmaxf(c, 0.f), 1.f);
+    return c <= 0.0031308f ? 12.92f * c : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+}
+__device__ __forceinline__ float lab_f(float t) { return t > 0.008856f ? cbrtf(t) : 7.787f * t + 16.0f / 116.0f; }
+__device__ __forceinline__ float3 bgr_to_lab(float b, float g, float r) {
+    const float R = srgb_to_linear(r), G = srgb_to_linear(g), B = srgb_to_linear(b);
+    const float X = (0.412453f * R + 0.357580f * G + 0.180423f * B) * (1.0f / 0.950456f);
+    const float Y = 0.212671f * R + 0.715160f * G + 0.072169f * B;
+    const float Z = (0.019334f * R + 0.119193f * G + 0.950227f * B) * (1.0f / 1.088754f);
+    const float fx = lab_f(X), fy = lab_f(Y), fz = lab_f(Z);
+    const float L = Y > 0.008856f ? 116.0f * fy - 16.0f : 903.3f * Y;
+    return make_float3(L, 500.0f * (fx - fy), 200.0f * (fy - fz));
+}
+__device__ __forceinline__ float lab_finv(float t) {
+    return t > (7.787f * 0.008856f + 16.0f / 116.0f) ? t * t * t : (t - 16.0f / 116.0f) * (1.0f / 7.787f);
+}
+__device__ __forceinline__ float3 lab_to_bgr(float L, float a, float b) {
+    float fy, Y;
+    if (L <= 0.008856f * 903.3f) {
+        Y = L * (1.0f / 903.3f);
+        fy = 7.787f * Y + 16.0f / 116.0f;
+    } else {
+        fy = (L + 16.0f) * (1.0f / 116.0f);
+        Y = fy * fy * fy;
+    }
+    const float X = lab_finv(fy + a * (1.0f / 500.0f)) * 0.950456f;
+    const float Z = lab_finv(fy - b * (1.0f / 200.0f)) * 1.088754f;
+    const float R = 3.240479f * X - 1.537150f * Y - 0.498535f * Z;
+    const float G = -0.969256f * X + 1.875991f * Y + 0.041556f * Z;
+    const float B = 0.055648f * X - 0.204043f * Y + 1.057311f * Z;
+    return make_float3(linear_to_srgb(B), linear_to_srgb(G), linear_to_srgb(R));
+}
+
+// sums[img][0] += sum of L over the original image, sums[img][1] += sum of L over the restored image
+__global__ void wb_stats_kernel(const float* __restrict__ raw, long long ustride, const float2* __restrict__ ss,
+                                const uint8_t* __restrict__ orig_u8, const float* __restrict__ orig_f32, long long orig_ustride,
+                                double* sums, long long npx) {
+    const int img = blockIdx.y;
+    const float* r = raw + (long long)img * 3 * ustride;
+    const float2 k0 = ss[img * 3], k1 = ss[img * 3 + 1], k2 = ss[img * 3 + 2];
+    double so = 0.0, sd = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        float ob, og, orr;
+        if (orig_u8) {
+            const uint8_t* o = orig_u8 + ((long long)img * npx + i) * 3;
+            const float inv255 = (float)(1.0 / 255.0);
+            ob = (float)o[0] * inv255;
+            og = (float)o[1] * inv255;
+            orr = (float)o[2] * inv255;
+        } else {
+            const float* o = orig_f32 + (long long)img * 3 * orig_ustride + i;
+            ob = o[0];
+            og = o[orig_ustride];
+            orr = o[2 * orig_ustride];
+        }
+        so += (double)bgr_to_lab(ob, og, orr).x;
+        const float nb = fmaf(r[i], k0.x, k0.y), ng = fmaf(r[ustride + i], k1.x, k1.y), nr = fmaf(r[2 * ustride + i], k2.x, k2.y);
+        sd += (double)bgr_to_lab(nb, ng, nr).x;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        so += __shfl_xor_sync(0xffffffffu, so, o);
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    }
+    __shared__ double red[8][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        red[warp][0] = so;
+        red[warp][1] = sd;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            a += red[w][0];
+            b += red[w][1];
+        }
+        atomicAdd(&sums[2 * img], a);
+        atomicAdd(&sums[2 * img + 1], b);
+    }
+}
+
+__global__ void wb_apply_kernel(const float* __restrict__ raw, long long ustride, const float2* __restrict__ ss,
+                                const double* __restrict__ sums, uint8_t* __restrict__ out, long long npx) {
+    const int img = blockIdx.y;
+    const float* r = raw + (long long)img * 3 * ustride;
+    uint8_t* o = out + (long long)img * npx * 3;
+    const float2 k0 = ss[img * 3], k1 = ss[img * 3 + 1], k2 = ss[img * 3 + 2];
+    // gain = avgL_orig / (avgL_deblur + 1e-6) in double (utils.hpp:60-62); applied as a float factor
+    const float gain = (float)((sums[2 * img] / (double)npx) / (sums[2 * img + 1] / (double)npx + 1e-6));
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (long long)gridDim.x * blockDim.x) {
+        const float nb = fmaf(r[i], k0.x, k0.y), ng = fmaf(r[ustride + i], k1.x, k1.y), nr = fmaf(r[2 * ustride + i], k2.x, k2.y);
+        float3 lab = bgr_to_lab(nb, ng, nr);
+        lab.x = fminf(fmaxf(lab.x * gain, 0.0f), 100.0f);
+        const float3 bgr = lab_to_bgr(lab.x, lab.y, lab.z);
+        o[3 * i] = (uint8_t)min(max(__float2int_rn(bgr.x * 255.0f), 0), 255);
+        o[3 * i + 1] = (uint8_t)min(max(__float2int_rn(bgr.y * 255.0f), 0), 255);
+        o[3 * i + 2] = (uint8_t)min(max(__float2int_rn(bgr.z * 255.0f), 0), 255);
+    }
+}
+
+cudaError_t launch_white_balance_pack_u8(const float* raw, long long raw_unit_stride, const float2* scale_shift,
+                                         const uint8_t* orig_u8, const float* orig_f32, long long orig_unit_stride, double* sums,
+                                         uint8_t* out, int imgs, int rows, int cols, cudaStream_t s) {
+    const long long npx = (long long)rows * cols;
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * imgs, s);
+    if (e != cudaSuccess) return e;
+    int bx = (int)((npx + 255) / 256);
+    if (bx > 148 * 4) bx = 148 * 4;
+    dim3 g(bx, imgs);
+    wb_stats_kernel<<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, orig_u8, orig_f32, orig_unit_stride, sums, npx);
+    wb_apply_kernel<<<g, 256, 0, s>>>(raw, raw_unit_stride, scale_shift, sums, out, npx);
+    return cudaGetLastError();
+}
+
 // Pass 4b: normalised f32 planes (what fft_gpu::wienerDeblur_RGB_* hands back, fft_gpu.cu:379-384).
 __global__ void normalize_f32_kernel(const float* raw, long long ustride, const float2* ss, float* out,
                                      long long ostride, long long npx) {

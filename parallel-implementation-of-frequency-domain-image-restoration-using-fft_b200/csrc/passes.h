@@ -103,6 +103,10 @@ cudaError_t launch_minmax_finalize(const unsigned int* minmax, float2* scale_shi
 // u8 interleaved [img][H][W][C] from raw planes of local units img*C + c
 cudaError_t launch_pack_u8(const float* raw, long long raw_unit_stride, const float2* scale_shift, uint8_t* out,
                            int imgs, int channels, int rows, int cols, cudaStream_t s);
+// Lab white balance + 8-bit pack for 3-channel images (gpu.cpp:123-134); orig_u8 or orig_f32 is the blurred input
+cudaError_t launch_white_balance_pack_u8(const float* raw, long long raw_unit_stride, const float2* scale_shift,
+                                         const uint8_t* orig_u8, const float* orig_f32, long long orig_unit_stride, double* sums,
+                                         uint8_t* out, int imgs, int rows, int cols, cudaStream_t s);
 // normalised f32 planes [unit][H][W]
 cudaError_t launch_normalize_f32(const float* raw, long long raw_unit_stride, const float2* scale_shift, float* out,
                                  long long out_unit_stride, int units, int rows, int cols, cudaStream_t s);

@@ -55,6 +55,8 @@ def lib():
             "fdr_plan_destroy": [vp],
             "fdr_plan_padded_size": [vp, C.POINTER(i), C.POINTER(i)],
             "fdr_plan_set_chunk_images": [vp, i],
+            "fdr_plan_set_white_balance": [vp, i],
+            "fdr_white_balance_pack_host": [C.POINTER(_fp), C.POINTER(_fp), i, i, vp],
             "fdr_plan_set_psf_host": [vp, _fp, i, i, sz, f],
             "fdr_plan_set_psf_motion": [vp, i, d, f],
             "fdr_plan_get_psf_host": [vp, _fp, i, C.POINTER(i), C.POINTER(i)],
@@ -176,6 +178,9 @@ class Plan:
 
     def set_chunk_images(self, n):
         _check(lib().fdr_plan_set_chunk_images(self.h, n))
+
+    def set_white_balance(self, on=True):
+        _check(lib().fdr_plan_set_white_balance(self.h, int(on)))
 
     def set_psf(self, psf, K=0.01):
         psf = _f32(psf)
@@ -357,6 +362,18 @@ class Shard:
         n = C.c_longlong(0)
         _check(lib().fdr_shard_last_launch_count(self.h, C.byref(n)))
         return n.value
+
+
+def white_balance_pack(restored_planes, original_planes):
+    """gpu.cpp:123-134 on the device: 3 restored + 3 original f32 planes (B, G, R) -> u8 (rows, cols, 3)."""
+    r = [_f32(p) for p in restored_planes]
+    o = [_f32(p) for p in original_planes]
+    rows, cols = r[0].shape
+    out = np.empty((rows, cols, 3), np.uint8)
+    rp = (_fp * 3)(*[_p(a) for a in r])
+    op = (_fp * 3)(*[_p(a) for a in o])
+    _check(lib().fdr_white_balance_pack_host(rp, op, rows, cols, out.ctypes.data))
+    return out
 
 
 def memcpy(dst, src, nbytes, kind):

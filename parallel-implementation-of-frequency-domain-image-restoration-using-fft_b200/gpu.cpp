@@ -6,7 +6,7 @@
 // fresh copy of the input (the reference filters `channels` in place three times), the serial
 // baseline is printed only when the reference's serial translation unit is linked in
 // (-DFDR_WITH_REFERENCE_SERIAL), and an optional 4th argument writes the restored 8-bit image
-// (direct x255 pack of the normalised planes; the Lab white-balance stage is a later row).
+// (after the same Lab white-balance post stage as the reference, gpu.cpp:123-134, run on the device).
 #include <cstdlib>
 #include <iostream>
 
@@ -83,9 +83,21 @@ int main(int argc, char** argv) {
     if (serial_time > 0) printf("[Speedup] %.2fx ms\n", serial_time / gpu_time);
 
     if (argc == 5) {
-        Mat merged_float, out8;
-        merge(result, merged_float);
-        merged_float.convertTo(out8, CV_8U, 255.0);
+        // gpu.cpp:123-134: Lab white balance against the blurred input, then 8-bit -- on the device
+        Mat out8(img.rows, img.cols, CV_8UC3);
+        vector<Mat> rc(3), oc(3);
+        const float* rp[3];
+        const float* op[3];
+        for (int i = 0; i < 3; ++i) {
+            rc[i] = result[i].isContinuous() ? result[i] : result[i].clone();
+            oc[i] = input[i].isContinuous() ? input[i] : input[i].clone();
+            rp[i] = rc[i].ptr<float>(0);
+            op[i] = oc[i].ptr<float>(0);
+        }
+        if (fdr_white_balance_pack_host(rp, op, img.rows, img.cols, out8.ptr<unsigned char>(0)) != FDR_OK) {
+            cerr << "Error: " << __FILE__ << ":" << __LINE__ << ", " << fdr_last_error() << endl;
+            return 1;
+        }
         if (!imwrite(argv[4], out8)) {
             cout << "Cannot write image\n";
             return -1;
