@@ -136,13 +136,28 @@ def run_reference(args):
     psf = O.port().motion_psf(plen, pang)
     have_ref = O.have_ref()
     threads = os.cpu_count() or 1
-    mode = "openmp" if have_ref else "serial"
+    mode = args.ref_mode if have_ref else "serial"
     sample = max(1, min(images, args.ref_images))
-    for _ in range(args.warmup):
-        cpu_restore_images(O, mode, cfg_idx, 0, 1, H, W, psf, threads)
-    t = 0.0
-    for s in range(args.steps):
-        t += cpu_restore_images(O, mode, cfg_idx, s * sample, sample, H, W, psf, threads)
+    if mode == "mpi":
+        # the reference's MPI backend over the single-node stand-in (oracle/mpi_standin), ranks = host cores (max 16)
+        import numpy as np
+        ranks = max(1, min(threads, 16))
+        t = 0.0
+        for s in range(args.warmup + args.steps):
+            tt = 0.0
+            for i in range(s * sample, (s + 1) * sample):
+                img = O.synth_image_u8(cfg_idx, i, H, W)
+                planes = np.stack([O.pad_pow2(img[c].astype(np.float32) * np.float32(1.0 / 255.0)) for c in range(3)])
+                tt += O.ref_mpi_wiener(planes, psf, K_WIENER, ranks)[1] * 1e-3
+            if s >= args.warmup:
+                t += tt
+        threads = ranks
+    else:
+        for _ in range(args.warmup):
+            cpu_restore_images(O, mode, cfg_idx, 0, 1, H, W, psf, threads)
+        t = 0.0
+        for s in range(args.steps):
+            t += cpu_restore_images(O, mode, cfg_idx, s * sample, sample, H, W, psf, threads)
     mpx = sample * H * W * args.steps / t / 1e6
     line = {
         "impl": "reference", "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
@@ -151,7 +166,7 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "images_per_step_sample": sample, "image": [H, W, 3], "psf": [plen, pang],
                    "K": K_WIENER},
-        "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": threads if mode == "openmp" else 1,
+        "cpu_baseline": {"value": mpx, "unit": "Mpixel/s", "cores": threads if mode in ("openmp", "mpi") else 1,
                          "kind": "reference" if have_ref else "port",
                          "sample": "%d image(s) of %dx%dx3 per step, reference %s mode (fft_%s.cpp compiled unmodified)"
                                    % (sample, H, W, mode, mode)},
@@ -331,6 +346,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-images", type=int, default=128, help="images per rank per end-to-end step (bounds pinned host memory)")
     ap.add_argument("--ref-images", type=int, default=2, help="--impl reference: images per step")
+    ap.add_argument("--ref-mode", default="openmp", choices=["openmp", "serial", "simd", "mpi"],
+                    help="--impl reference: which of the reference's CPU modes to time (default: openmp, all host threads)")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")

@@ -15,8 +15,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <iostream>
+#include <map>
 #include <memory>
+#include <string>
 #include <vector>
 
 #define CV_PI 3.1415926535897932384626433832795
@@ -100,9 +103,11 @@ class Mat {
 public:
     int rows, cols;
     uchar* data;
+    const uchar* datastart;  // whole allocation (fft_mpi.cpp:363 copies [datastart, dataend))
+    const uchar* dataend;
     size_t step;  // bytes between consecutive rows
 
-    Mat() : rows(0), cols(0), data(nullptr), step(0), type_(CV_32F) {}
+    Mat() : rows(0), cols(0), data(nullptr), datastart(nullptr), dataend(nullptr), step(0), type_(CV_32F) {}
     Mat(int r, int c, int type) : Mat() { create(r, c, type); }
     Mat(Size s, int type) : Mat() { create(s.height, s.width, type); }
 
@@ -116,6 +121,8 @@ public:
         size_t bytes = step * (size_t)r;
         store_ = std::shared_ptr<uchar>(static_cast<uchar*>(std::malloc(bytes ? bytes : 1)), std::free);
         data = store_.get();
+        datastart = data;
+        dataend = data + bytes;
     }
 
     static Mat zeros(int r, int c, int type) {
@@ -148,6 +155,8 @@ public:
         v.type_ = type_;
         v.step = step;
         v.store_ = store_;
+        v.datastart = datastart;
+        v.dataend = dataend;
         v.data = data + step * (size_t)roi.y + elemSize() * (size_t)roi.x;
         return v;
     }
@@ -208,6 +217,15 @@ inline Mat operator-(const Mat& a) {
 inline Mat operator+(const Mat& a, const Scalar& s) {
     const float k = (float)s.val[0];
     return shim_detail::unary_f32(a, [k](float x) { return x + k; });
+}
+// m /= s : OpenCV evaluates it as m * (1/s) through convertTo (one rounding of the float factor)
+inline Mat& operator/=(Mat& a, double s) {
+    const float k = (float)(1.0 / s);
+    for (int r = 0; r < a.rows; ++r) {
+        float* p = a.ptr<float>(r);
+        for (int c = 0; c < a.cols * a.channels(); ++c) p[c] = p[c] * k;
+    }
+    return a;
 }
 inline Mat operator*(const Mat& a, double s) {
     const float k = (float)s;

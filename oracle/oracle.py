@@ -205,6 +205,34 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+REF_MPI_BIN = os.path.join(HERE, "_ref", "ref_mpi_bench")
+
+
+def have_ref_mpi():
+    return os.path.exists(REF_MPI_BIN)
+
+
+def ref_mpi_wiener(planes, psf, K=0.01, nprocs=2):
+    """The reference's MPI backend (fft_mpi.cpp compiled unmodified over oracle/mpi_standin) on `nprocs`
+    forked ranks, driven like mpi.cpp:95-111.  planes: (n, Rp, Cp) f32, already padded to powers of two.
+    Returns (normalised planes, wall ms of the channel loop on rank 0)."""
+    import tempfile
+    planes = np.ascontiguousarray(planes, dtype=np.float32)
+    psf = _f32(psf)
+    n, r, c = planes.shape
+    with tempfile.TemporaryDirectory() as d:
+        pin, ppsf, pout = (os.path.join(d, x) for x in ("in.f32", "psf.f32", "out.f32"))
+        planes.tofile(pin)
+        psf.tofile(ppsf)
+        res = subprocess.run([REF_MPI_BIN, str(int(nprocs)), pin, str(n), str(r), str(c), ppsf, str(psf.shape[0]), repr(float(K)), pout],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("ref_mpi_bench failed: " + res.stderr[-500:])
+        ms = [float(ln.split()[1]) for ln in res.stdout.splitlines() if ln.startswith("mpi_ms")][-1]
+        out = np.fromfile(pout, np.float32).reshape(n, r, c)
+    return out, ms
+
+
 # ---- helpers shared by tests and bench (pure numpy, follow the reference drivers) ----
 
 def pad_pow2(plane):

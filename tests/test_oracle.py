@@ -86,6 +86,21 @@ def test_port_bit_exact_vs_compiled_reference(oracle):
         assert np.abs(R.wiener(img, psf, 0.01, "simd") - b).max() < 1e-5
 
 
+def test_reference_mpi_mode_over_standin(oracle):
+    """fft_mpi.cpp compiled unmodified over the single-node MPI stand-in: 1, 2 and 3
+    forked ranks (3 does not divide the rows: calculate_distribution remainder path, fft_mpi.cpp:89-100)
+    agree with the serial mode within the reference's own self-check tolerance (mpi.cpp:11-35)."""
+    if not oracle.have_ref_mpi() or not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(5)
+    planes = np.stack([rng.random((64, 128), dtype=np.float32) for _ in range(2)])
+    psf = oracle.port().motion_psf(9, 30.0)
+    want = np.stack([oracle.ref().wiener(pl, psf, 0.01, "serial") for pl in planes])
+    for nprocs in (1, 2, 3):
+        got, ms = oracle.ref_mpi_wiener(planes, psf, 0.01, nprocs)
+        assert ms > 0 and np.abs(got - want).max() < 1e-5, nprocs
+
+
 def test_oracle_accuracy_against_float64(oracle):
     """The oracle's own error vs an exact pipeline is ~1e-6..1e-5, far
     inside the 1e-4 gate, so an accurate-twiddle GPU FFT can meet the gate against it."""
