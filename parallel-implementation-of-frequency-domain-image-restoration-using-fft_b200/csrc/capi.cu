@@ -789,12 +789,13 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     FDR_TRY(ensure_device(p->device));
     const int nu = 2 * npairs;
     FDR_TRY(ensure_workspace(p, nu));
-    FDR_TRY(p->d_in_u8.ensure((size_t)nu * p->H * p->W));
+    const int n_img = (nu + 2) / 3;  // interleaved BGR images, as the real pipeline sees them
+    FDR_TRY(p->d_in_u8.ensure((size_t)n_img * 3 * p->H * p->W));
     cudaStream_t s = p->stream;
-    FDR_CUDA(launch_synth_u8(p->d_in_u8.p, 12345u, 0, 1, nu, (long long)p->H * p->W, 0, (long long)p->H * p->W, s));
+    FDR_CUDA(launch_synth_u8(p->d_in_u8.p, 12345u, 0, n_img, 3, (long long)p->H * p->W, 0, (long long)p->H * p->W, s));
     RowPassArgs r1{};
     r1.n = p->Cp; r1.nrows = p->H; r1.npairs = npairs; r1.in_mode = ROW_IN_PAIR_U8; r1.out_mode = ROW_OUT_COMPLEX;
-    r1.in_u8 = p->d_in_u8.p; r1.channels = nu; r1.img_rows = p->H; r1.img_cols = p->W; r1.units_total = nu;
+    r1.in_u8 = p->d_in_u8.p; r1.channels = 3; r1.img_rows = p->H; r1.img_cols = p->W; r1.units_total = nu;
     r1.cout = p->spec.p; r1.cplane = (long long)p->plane_elems(); r1.tw = p->tw_rows;
     ColPassArgs c2{};
     c2.n = p->Rp; c2.pitch = p->Cp; c2.npairs = npairs; c2.rows_valid = p->H; c2.data = p->spec.p;

@@ -7,6 +7,13 @@
 
 namespace fdr {
 
+// u8 -> float * k without the conversion pipe: 0x4B000000 | b is the float 2^23 + b exactly, so
+// fma(2^23 + b, k, -(2^23 * k)) = b*k with ONE rounding of b*k (2^23*k is exact for k = (float)(1/255): a
+// power-of-two multiple), i.e. bit-identical to (float)b * k.
+__device__ __forceinline__ float u8_scaled(uint8_t b, float k, float neg_bias) {
+    return fmaf(__uint_as_float(0x4B000000u | (unsigned int)b), k, neg_bias);
+}
+
 __device__ __forceinline__ unsigned int f32_ordered(float f) {
     unsigned int b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
@@ -92,9 +99,10 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLO
             const uint8_t* p0 = a.in_u8 + ((i0 * a.img_rows + row) * (long long)a.img_cols) * 3 + c0 + 3 * t;
             const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row) * (long long)a.img_cols) * 3 + c1 + 3 * t;
             if (active && a.img_cols == N) {
+                const float nb0 = -8388608.0f * inv255, nb1 = -8388608.0f * k1;
 #pragma unroll
                 for (int m = 0; m < E; ++m)
-                    v[m] = make_float2((float)__ldg(p0 + 3 * T * m) * inv255, (float)__ldg(p1 + 3 * T * m) * k1);
+                    v[m] = make_float2(u8_scaled(__ldg(p0 + 3 * T * m), inv255, nb0), u8_scaled(__ldg(p1 + 3 * T * m), k1, nb1));
             } else {
 #pragma unroll
                 for (int m = 0; m < E; ++m) {
