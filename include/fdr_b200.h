@@ -114,7 +114,7 @@ int fdr_plan_set_kernel_timing(fdr_plan* plan, int enabled);
 int fdr_plan_get_kernel_timing(fdr_plan* plan, double total_ms[4], long long launches[4], double bytes[4]);
 /* Timing probe for kernel work: runs one pass `reps` times back to back on a synthetic workspace
  * of `npairs` plane pairs and returns the mean device time in ms.  pass 1 = rows forward,
- * 2 = columns (variant 0 = Wiener default, 1 = Wiener non-persistent, 2 = single forward FFT,
+ * 2 = columns (variant 0 = Wiener default (TMA tiles), 1 = Wiener with plain loads, 2 = single forward FFT,
  * 3 = load+store only), 3 = rows inverse + min/max. */
 int fdr_plan_time_pass(fdr_plan* plan, int pass, int variant, int npairs, int reps, float* ms_avg);
 /* Number of kernels the most recent restore call launched. */

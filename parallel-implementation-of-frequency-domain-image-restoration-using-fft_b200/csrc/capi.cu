@@ -65,7 +65,6 @@ struct fdr_plan {
     DevBuf<float2> wiener_nat;    // natural-order copy, built lazily for the parity-gate API of long-column plans
     bool col_split = false;       // long columns: four-step column pass (col_split.cuh)
     DevBuf<float> psf;            // psf_rows x psf_cols
-    int persistent_sms = 0;           // SM count when the persistent column kernel is enabled
     int lanes = 4;                    // chunks in flight on separate streams (FDR_LANES=1..4)
     cudaStream_t lane_stream[4] = {};
     cudaEvent_t lane_fork = nullptr, lane_join[4] = {};
@@ -242,7 +241,6 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         c2.wiener = p->wiener.p;
         c2.K = p->K;
         c2.tw = p->tw_cols;
-        c2.persistent_sms = p->persistent_sms;
         {
             KernelTimer kt(p, s, 1, (8.0 * p->H * p->Cp + 16.0 * P) * np);
             if (p->col_split) {
@@ -447,10 +445,6 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
     p->Rp = next_pow2(rows);
     p->Cp = next_pow2(cols);
     {
-        int sms = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        const char* env = getenv("FDR_COL_PERSISTENT");
-        p->persistent_sms = (env && atoi(env) != 0) ? sms : 0;  // opt-in: measured slower than 2 CTAs/SM
         {
             ColPassArgs probe{};
             probe.n = p->Rp;
@@ -461,8 +455,6 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
         }
         const char* ln = getenv("FDR_LANES");
         if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) p->lanes = atoi(ln);
-        const char* fg = getenv("FDR_L2_FETCH");
-        if (fg && atoi(fg) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg));
     }
     cudaError_t e = get_twiddles(p->Cp, &p->tw_rows);
     if (e == cudaSuccess) e = get_twiddles(p->Rp, &p->tw_cols);
@@ -781,7 +773,7 @@ __attribute__((visibility("default"))) int fdr_plan_get_kernel_timing(fdr_plan* 
 
 // Timing probe: runs one pass `reps` times on a workspace of `npairs` plane pairs and returns the
 // mean device time.  pass: 1 = rows forward (u8 in), 2 = columns, 3 = rows inverse + min/max.
-// variant (pass 2): 0 = Wiener, default dispatch; 1 = Wiener, non-persistent kernel; 2 = one forward FFT;
+// variant (pass 2): 0 = Wiener, default dispatch (TMA tiles); 1 = Wiener, plain-load kernel; 2 = one forward FFT;
 // 3 = load + store only.
 __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int pass, int variant, int npairs, int reps, float* ms_avg) {
     if (!p || !ms_avg || npairs < 1 || reps < 1) return set_error(FDR_E_INVALID, "bad arguments");
@@ -801,7 +793,7 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     c2.n = p->Rp; c2.pitch = p->Cp; c2.npairs = npairs; c2.rows_valid = p->H; c2.data = p->spec.p;
     c2.cplane = (long long)p->plane_elems(); c2.wiener = p->wiener.p; c2.K = p->K; c2.tw = p->tw_cols;
     c2.mode = variant == 2 ? COL_FFT : variant == 3 ? COL_COPY : COL_WIENER;
-    c2.persistent_sms = (variant == 0) ? p->persistent_sms : 0;
+    c2.plain_loads = (variant == 1) ? 1 : 0;
     RowPassArgs r3{};
     r3.n = p->Cp; r3.nrows = p->Rp; r3.npairs = npairs; r3.in_mode = ROW_IN_COMPLEX; r3.out_mode = ROW_OUT_REAL_PAIR;
     r3.cin = p->spec.p; r3.cplane = (long long)p->plane_elems(); r3.units_total = nu; r3.raw = p->raw.p;

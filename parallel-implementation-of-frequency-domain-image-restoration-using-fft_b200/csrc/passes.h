@@ -73,7 +73,7 @@ struct ColPassArgs {
     const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
     float2* wiener_out;   // COL_MAKE_WIENER
     float K;
-    int persistent_sms;   // COL_WIENER: > 0 selects the persistent cp.async kernel with this many CTAs
+    int plain_loads;      // COL_WIENER: 1 = force the plain-load kernel instead of the TMA one (timing probe)
 };
 
 // Launchers (defined in passes_*.cu).  Return cudaGetLastError() of the launch.

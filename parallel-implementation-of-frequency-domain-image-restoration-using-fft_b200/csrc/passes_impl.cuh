@@ -314,111 +314,6 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
     }
 }
 
-// ---------------------------------------------------------------------------------
-// Pair-loop column pass (COL_WIENER only; N*CW*8 B = 64 KB tiles, 64 <= N <= 4096).
-// A CTA owns one column group at a time and walks all plane pairs of the launch for it:
-//   * the group's Wiener-factor tile is fetched ONCE into shared memory (cp.async) and reused for
-//     every pair -- Wf traffic drops from 8 B to 8/pairs B per pixel and leaves the load path;
-//   * the NEXT pair's data tile is loaded into a second register set while the current one is
-//     transformed, so global-load latency is hidden behind the two FFTs instead of serialised;
-//   * results go straight from registers to global memory.
-// Shared memory: exchange buffer + Wiener tile = 2 x 64 KB, one CTA per SM, <= 96 registers so row-pass
-// CTAs of other chunks (other streams) can still co-reside.
-// ---------------------------------------------------------------------------------
-template <int LOGN> struct ColPersistGeom {
-    static constexpr int N = 1 << LOGN;
-    static constexpr int E = FftGeom<N>::E;
-    static constexpr int T = FftGeom<N>::T;
-    static constexpr int CW = (N >= 256) ? (8192 / N) : 32;
-    static constexpr int THREADS = T * CW;
-    static constexpr size_t TILE = (size_t)N * CW * sizeof(float2);
-    static constexpr size_t SMEM = 2 * TILE;
-    static constexpr int CHUNKS_PER_ROW = CW * 8 / 16;  // 16-byte cp.async chunks per tile row
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-template <int LOGN>
-__global__ void __launch_bounds__(ColPersistGeom<LOGN>::THREADS, 1) col_wiener_persistent_kernel(const ColPassArgs a) {
-    using Gm = ColPersistGeom<LOGN>;
-    constexpr int N = Gm::N, E = Gm::E, T = Gm::T, CW = Gm::CW, CPR = Gm::CHUNKS_PER_ROW;
-    extern __shared__ float2 smem2[];
-    float2* ex = smem2;                     // exchange buffer
-    float2* wsm = smem2 + (size_t)N * CW;   // [N][CW] Wiener tile of the current group
-    const int tid = threadIdx.x;
-    const int c = tid % CW, t = tid / CW;
-    const int ngroups = a.pitch / CW;
-    const long long stride = (long long)T * a.pitch;
-
-    auto load_tile = [&](float2 (&dst)[E], int g, int p) {
-        const float2* src = a.data + (long long)(p + a.pair_base) * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
-#pragma unroll
-        for (int m = 0; m < E; ++m) dst[m] = (t + T * m < a.rows_valid) ? src[m * stride] : make_float2(0.f, 0.f);
-    };
-
-    float2 v[E], nx[E];
-    int g = blockIdx.x;
-    if (g >= ngroups) return;
-    load_tile(v, g, 0);
-    while (g < ngroups) {
-        // Wiener tile of this group -> shared memory
-        {
-            const float2* src = a.wiener + (long long)g * CW;
-            for (int q = tid; q < N * CPR; q += Gm::THREADS) {
-                const int row = q / CPR, part = q % CPR;
-                cp_async16(wsm + (size_t)row * CW + part * 2, src + (long long)row * a.pitch + part * 2);
-            }
-            cp_async_commit();
-        }
-        const int g_next = g + gridDim.x;
-        for (int p = 0; p < a.npairs; ++p) {
-            // prefetch the next tile (next pair of this group, or pair 0 of this CTA's next group)
-            const bool more = (p + 1 < a.npairs) || (g_next < ngroups);
-            if (more) load_tile(nx, (p + 1 < a.npairs) ? g : g_next, (p + 1 < a.npairs) ? p + 1 : 0);
-            fft_forward<N, CW>(v, ex, a.tw, t, c);
-            if (p == 0) {
-                cp_async_wait_all();
-                __syncthreads();
-            }
-#pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const float2 y = cmul(v[m], wsm[(size_t)(t + T * m) * CW + c]);
-                v[m] = make_float2(y.x, -y.y);
-            }
-            fft_forward<N, CW>(v, ex, a.tw, t, c);
-            float2* base = a.data + (long long)(p + a.pair_base) * a.cplane + (long long)t * a.pitch + (long long)g * CW + c;
-#pragma unroll
-            for (int m = 0; m < E; ++m) base[m * stride] = v[m];
-#pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = nx[m];
-        }
-        __syncthreads();  // everyone is done with this group's Wiener tile
-        g = g_next;
-    }
-}
-
-template <int LOGN> cudaError_t launch_col_wiener_persistent(const ColPassArgs& a, int num_sms, cudaStream_t s) {
-    using Gm = ColPersistGeom<LOGN>;
-    static unsigned long long configured = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured >> (dev & 63) & 1ULL)) {
-        cudaError_t e = cudaFuncSetAttribute(col_wiener_persistent_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
-        if (e != cudaSuccess) return e;
-        configured |= 1ULL << (dev & 63);
-    }
-    const int ngroups = a.pitch / Gm::CW;
-    int grid = num_sms;
-    if (grid > ngroups) grid = ngroups;
-    col_wiener_persistent_kernel<LOGN><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
-    return cudaGetLastError();
-}
-
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row_variant(const RowPassArgs& a, cudaStream_t s) {
     using Gm = RowGeom<LOGN>;
     if (Gm::SMEM > 48 * 1024) {
@@ -473,12 +368,7 @@ template <int LOGN, int CW> cudaError_t launch_col_pass_t(const ColPassArgs& a, 
     switch (a.mode) {
         case COL_FFT:
             return a.conj ? launch_col_variant<LOGN, CW, COL_FFT, true>(a, s) : launch_col_variant<LOGN, CW, COL_FFT, false>(a, s);
-        case COL_WIENER:
-            if constexpr (LOGN >= 6 && LOGN <= 12) {
-                if (a.persistent_sms > 0 && a.pitch % ColPersistGeom<LOGN>::CW == 0)
-                    return launch_col_wiener_persistent<LOGN>(a, a.persistent_sms, s);
-            }
-            return launch_col_variant<LOGN, CW, COL_WIENER, false>(a, s);
+        case COL_WIENER: return launch_col_variant<LOGN, CW, COL_WIENER, false>(a, s);
         case COL_MAKE_WIENER: return launch_col_variant<LOGN, CW, COL_MAKE_WIENER, false>(a, s);
         case COL_FILTER: return launch_col_variant<LOGN, CW, COL_FILTER, false>(a, s);
         case COL_COPY: return launch_col_variant<LOGN, CW, COL_COPY, false>(a, s);

@@ -52,7 +52,6 @@ struct fdr_shard {
     const float2* tw_rows = nullptr;
     const float2* tw_cols = nullptr;
     long long launches = 0;
-    int persistent_sms = 0;
     bool col_split = false;
 };
 
@@ -138,12 +137,6 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
         probe.mode = COL_WIENER;
         const char* cs = getenv("FDR_COL_SPLIT");
         s->col_split = col_split_applicable(probe) && !(cs && atoi(cs) == 0);
-    }
-    {
-        int sms = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        const char* env = getenv("FDR_COL_PERSISTENT");
-        s->persistent_sms = (env && atoi(env) != 0) ? sms : 0;
     }
     int rc = FDR_OK;
     cudaError_t e = get_twiddles(Cp, &s->tw_rows);
@@ -338,7 +331,6 @@ FDR_API int fdr_shard_phase2_pairs(fdr_shard* s, int pair_first, int pair_count,
     c.wiener = s->wiener.p;
     c.K = s->K;
     c.tw = s->tw_cols;
-    c.persistent_sms = s->persistent_sms;
     if (s->col_split) {
         int nl = 0;
         FDR_CUDA(launch_col_split(c, pick(s, stream), &nl));

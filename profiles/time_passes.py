@@ -13,5 +13,5 @@ with fdr.Plan(n, n, 3) as p:
         def gbs(ms, bpp): return px * bpp / (ms * 1e-3) / 1e9
         r1 = p.time_pass(1, 0, npairs); r3 = p.time_pass(3, 0, npairs)
         c0 = p.time_pass(2, 0, npairs); c1 = p.time_pass(2, 1, npairs); c2 = p.time_pass(2, 2, npairs); c3 = p.time_pass(2, 3, npairs)
-        print("N=%d pairs=%d | per pair: pass1 %.1f us (%.0f GB/s) | pass3 %.1f us (%.0f GB/s) | pass2 default %.1f us (%.0f GB/s), alt %.1f us, single FFT %.1f us, copy-only %.1f us (%.0f GB/s)"
+        print("N=%d pairs=%d | per pair: pass1 %.1f us (%.0f GB/s) | pass3 %.1f us (%.0f GB/s) | pass2 default %.1f us (%.0f GB/s), plain-load kernel %.1f us, single FFT %.1f us, copy-only %.1f us (%.0f GB/s)"
               % (n, npairs, r1 * 1e3 / npairs, gbs(r1, 10), r3 * 1e3 / npairs, gbs(r3, 16), c0 * 1e3 / npairs, gbs(c0, 24), c1 * 1e3 / npairs, c2 * 1e3 / npairs, c3 * 1e3 / npairs, gbs(c3, 16)))
