@@ -437,7 +437,8 @@ def main():
     ktimes = plan.kernel_timing()
     plan.set_kernel_timing(False)
     # the same kernels timed ALONE (no other chunk in flight), CUDA events inside the library
-    iso_pairs = 3
+    l2 = ktimes["pass2_cols_wiener"]["launches"] / max(1, args.steps)  # pass-2 launches per step = chunks per step
+    iso_pairs = max(1, int(round((B * 3 / 2.0) / max(1.0, l2))))           # plane pairs per launch inside the step
     isolated = {"pairs_per_launch": iso_pairs,
                 "pass1_ms": plan.time_pass(1, 0, iso_pairs, 10), "pass2_ms": plan.time_pass(2, 0, iso_pairs, 10),
                 "pass3_ms": plan.time_pass(3, 0, iso_pairs, 10)}
@@ -513,7 +514,7 @@ def main():
         "isolated_GBps": {k: iso_bytes[k] / (iso_ms[k] * 1e-3) / 1e9 for k in iso_ms},
         "in_step": {
             "note": "per-launch CUDA-event durations inside the timed region; chunks run on %s concurrent streams, so a launch's "
-                    "duration includes time shared with other chunks' kernels" % os.environ.get("FDR_LANES", "4"),
+                    "duration includes time shared with other chunks' kernels" % os.environ.get("FDR_LANES", "1"),
             "kernel_share_of_step": kd["ms"] / ksum if ksum else None,
             "dominant_GBps_per_launch": in_step_GBps,
             "dominant_GBps_share_normalised": kd["bytes"] / (ms_max * (kd["ms"] / ksum) * 1e-3) / 1e9 if ksum else None,

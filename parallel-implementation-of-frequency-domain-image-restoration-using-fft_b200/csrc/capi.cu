@@ -56,7 +56,7 @@ struct fdr_plan {
     // device workspace
     DevBuf<float2> spec;          // chunk pairs x Rp x Cp
     DevBuf<float> raw;            // chunk units x H x W
-    DevBuf<unsigned int> mm;      // chunk units x 2
+    DevBuf<unsigned int> mm;      // chunk units x FDR_MINMAX_SLOTS x 2
     DevBuf<float2> ss;            // chunk units
     DevBuf<float> mmf;            // chunk units x 2
     DevBuf<double> wb_sums;       // chunk images x 2 (Lab white balance)
@@ -65,7 +65,7 @@ struct fdr_plan {
     DevBuf<float2> wiener_nat;    // natural-order copy, built lazily for the parity-gate API of long-column plans
     bool col_split = false;       // long columns: four-step column pass (col_split.cuh)
     DevBuf<float> psf;            // psf_rows x psf_cols
-    int lanes = 4;                    // chunks in flight on separate streams (FDR_LANES=1..4)
+    int lanes = 1;                    // chunks in flight on separate streams (FDR_LANES=1..4); with large chunks one is best
     cudaStream_t lane_stream[4] = {};
     cudaEvent_t lane_fork = nullptr, lane_join[4] = {};
     int last_lane = 0;
@@ -91,16 +91,34 @@ struct fdr_plan {
     std::vector<cudaEvent_t> ev_pool;
 
     size_t plane_elems() const { return (size_t)Rp * Cp; }
-    // images per chunk: keep the complex workspace of a chunk near 96 MB (inside the 126 MB L2)
-    // but never below one image; an even unit count per chunk keeps plane pairs inside a chunk.
+    // Images per device chunk.  Measured on B200 (profiles/r1/chunk_sweep.txt): the passes are bound by the
+    // SM-side load/store pipe or by HBM, not helped by L2 residency between passes, and every launch pays
+    // a partial last wave -- so large chunks win: 32 images of 2048^2 (1.5 GB of spectrum) run 12 % faster
+    // than the 96 MB chunks that fit the L2.  An even unit count per chunk keeps plane pairs inside a chunk.
     int chunk_images(int n_images_total) const {
         int ci = chunk_images_user;
         if (ci <= 0) {
-            const double target = 96.0 * 1024 * 1024;
+            const double target = 1536.0 * 1024 * 1024;
             const double per_image = 0.5 * C * (double)plane_elems() * sizeof(float2);
             ci = (int)(target / per_image);
             if (ci < 1) ci = 1;
             const char* env = getenv("FDR_CHUNK_IMAGES");
+            if (env && atoi(env) > 0) ci = atoi(env);
+        }
+        if ((ci * C) % 2 && ci < n_images_total) ci += 1;
+        if (ci > n_images_total) ci = n_images_total;
+        return ci < 1 ? 1 : ci;
+    }
+    // Images per chunk of the pipelined HOST entry point: that path is PCIe-bound, so small chunks
+    // (about 75 MB of 8-bit input: 6 images of 2048^2) keep the fill and drain of the
+    // H2D -> compute -> D2H pipeline short; measured best among 2..32.
+    int host_chunk_images(int n_images_total) const {
+        int ci = chunk_images_user;
+        if (ci <= 0) {
+            const double per_image = (double)H * W * C;
+            ci = (int)(75.0e6 / per_image);
+            if (ci < 1) ci = 1;
+            const char* env = getenv("FDR_HOST_CHUNK_IMAGES");
             if (env && atoi(env) > 0) ci = atoi(env);
         }
         if ((ci * C) % 2 && ci < n_images_total) ci += 1;
@@ -155,7 +173,7 @@ int ensure_workspace(fdr_plan* p, int chunk_units) {
     const size_t L = (size_t)p->lanes;
     FDR_TRY(p->spec.ensure(L * pairs * p->plane_elems()));
     FDR_TRY(p->raw.ensure(L * chunk_units * p->H * p->W));
-    FDR_TRY(p->mm.ensure(L * chunk_units * 2));
+    FDR_TRY(p->mm.ensure(L * chunk_units * 2 * FDR_MINMAX_SLOTS));
     FDR_TRY(p->ss.ensure(L * chunk_units));
     FDR_TRY(p->mmf.ensure(L * chunk_units * 2));
     FDR_TRY(p->wb_sums.ensure(L * chunk_units * 2));
@@ -200,7 +218,7 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         if (L > 1) s = p->lane_stream[lane];
         float2* const spec_l = p->spec.p + (size_t)lane * ws_pairs * p->plane_elems();
         float* const raw_l = p->raw.p + (size_t)lane * p->ws_units * HW;
-        unsigned int* const mm_l = p->mm.p + (size_t)lane * p->ws_units * 2;
+        unsigned int* const mm_l = p->mm.p + (size_t)lane * p->ws_units * 2 * FDR_MINMAX_SLOTS;
         float2* const ss_l = p->ss.p + (size_t)lane * p->ws_units;
         float* const mmf_l = p->mmf.p + (size_t)lane * p->ws_units * 2;
         p->last_lane = lane;
@@ -666,7 +684,7 @@ __attribute__((visibility("default"))) int fdr_restore_images_host_u8(fdr_plan* 
     if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set: call fdr_plan_set_psf_* first");
     FDR_TRY(ensure_device(p->device));
     const size_t img_bytes = (size_t)p->H * p->W * p->C;
-    const int chunk = p->chunk_images(n_images);
+    const int chunk = p->host_chunk_images(n_images);
     const size_t chunk_bytes = img_bytes * chunk;
     for (int i = 0; i < 6; ++i) p->profile_ms[i] = 0.f;
     if (!p->s_in) {
@@ -773,8 +791,8 @@ __attribute__((visibility("default"))) int fdr_plan_get_kernel_timing(fdr_plan* 
 
 // Timing probe: runs one pass `reps` times on a workspace of `npairs` plane pairs and returns the
 // mean device time.  pass: 1 = rows forward (u8 in), 2 = columns, 3 = rows inverse + min/max.
-// variant (pass 2): 0 = Wiener, default dispatch (TMA tiles); 1 = Wiener, plain-load kernel; 2 = one forward FFT;
-// 3 = load + store only.
+// variant (pass 2): 0 = Wiener, default dispatch; 1 = Wiener, plain-load kernel; 2 = one forward FFT;
+// 3 = load + store only; 4 = Wiener, TMA kernel with one tile per CTA; 5 = Wiener, persistent pipelined TMA kernel.
 __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int pass, int variant, int npairs, int reps, float* ms_avg) {
     if (!p || !ms_avg || npairs < 1 || reps < 1) return set_error(FDR_E_INVALID, "bad arguments");
     if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
@@ -793,7 +811,7 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     c2.n = p->Rp; c2.pitch = p->Cp; c2.npairs = npairs; c2.rows_valid = p->H; c2.data = p->spec.p;
     c2.cplane = (long long)p->plane_elems(); c2.wiener = p->wiener.p; c2.K = p->K; c2.tw = p->tw_cols;
     c2.mode = variant == 2 ? COL_FFT : variant == 3 ? COL_COPY : COL_WIENER;
-    c2.plain_loads = (variant == 1) ? 1 : 0;
+    c2.col_variant = (variant == 1) ? 1 : (variant == 4) ? 2 : (variant == 5) ? 3 : 0;
     RowPassArgs r3{};
     r3.n = p->Cp; r3.nrows = p->Rp; r3.npairs = npairs; r3.in_mode = ROW_IN_COMPLEX; r3.out_mode = ROW_OUT_REAL_PAIR;
     r3.cin = p->spec.p; r3.cplane = (long long)p->plane_elems(); r3.units_total = nu; r3.raw = p->raw.p;

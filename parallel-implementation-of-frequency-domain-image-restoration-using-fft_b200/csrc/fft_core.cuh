@@ -10,12 +10,11 @@
 // (one coalesced 8-byte load each, L1-resident), computed once per device in double
 // precision -- no sincos or power products in the hot loop.
 //
-// Shared-memory layout of an exchange: float2 words, CW interleaved transforms,
-//   word(idx, c) = (idx ^ ((idx >> 4) & (16/CW - 1))) * CW + c.
-// For E = 16 this is bank-conflict free (64-bit accesses, half-warp phases) for the
-// scattered stage writes and the strided reads at every N and every CW (simulated
-// offline).  The XOR swizzle is linear over GF(2), so every access is
-// addr0 ^ compile-time-constant: one LOP3 per 8-byte LDS/STS.
+// Shared-memory layout of an exchange: float2 words, CW interleaved transforms, one skew group of CW
+// words after every 16 points:  word(idx, c) = (idx + (idx >> 4)) * CW + c   (struct Skew below).
+// For E = 16 this is bank-conflict free (64-bit accesses, half-warp phases) for the scattered stage
+// writes and the strided reads at every N and every CW (simulated offline), and every
+// access is thread base + compile-time offset: LDS/STS immediate offsets, no address arithmetic.
 //
 // Only the FORWARD transform (e^{-2 pi i nk/N}) is implemented; callers obtain the
 // inverse as conj(FFT(conj(x))), folding the conjugations into their load/store.
@@ -137,16 +136,20 @@ template <int N> struct FftGeom {
 };
 
 // ---------------------------------------------------------------------------------
-// Twiddle table of one length N: for every stage after the first, for every butterfly
-// b of the thread and every r = 1..R-1, T entries  exp(-2 pi i * r * k / (NS*R)),
-// k = (t + b*T) mod NS.  Offsets are compile-time.
+// Twiddle table of one length N: for every stage after the first and every r = 1..R-1 the factors
+// exp(-2 pi i * r * k / (NS*R)), k = (t + b*T) mod NS.  While NS <= T the index k = t mod NS does not
+// depend on the butterfly b and only NS distinct entries exist per r (layout [r][k]: the two half-warps
+// of a load coincide, one 128-byte wavefront); for NS > T the layout is [b][r][t].  Offsets are
+// compile-time.
 // ---------------------------------------------------------------------------------
 template <int N, int NS> struct TwStage {
     static constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T;
     static constexpr int REM = N / NS;
     static constexpr int R = (REM < E) ? REM : E;
     static constexpr int NB = E / R;
-    static constexpr int ENTRIES = (NS > 1) ? NB * (R - 1) * T : 0;
+    static constexpr bool SHARED_B = (NS <= T);          // k independent of b
+    static constexpr int PER_R = SHARED_B ? NS : T;      // entries per (b, r)
+    static constexpr int ENTRIES = (NS > 1) ? (SHARED_B ? 1 : NB) * (R - 1) * PER_R : 0;
     // table offset of this stage = entries of all earlier stages
 };
 // All stages before the last have radix 16 (greedy radices), so the stage with sub-length NS is
@@ -166,9 +169,26 @@ template <int N> struct TwTotal<N, N> {
     static constexpr int value = 0;
 };
 
-template <int CW> struct Swz {
-    static constexpr int G = (CW >= 16) ? 1 : 16 / CW;
-    __host__ __device__ static constexpr int f(int idx) { return idx ^ ((idx >> 4) & (G - 1)); }
+// Exchange-buffer layout: one skew group (CW words) is inserted after every 16 points when a point
+// group is narrower than a 128-byte bank row (CW < 16):  word(idx, c) = (idx + (idx >> 4)) * CW + c.
+// Every access of a stage is then  base(thread) + compile-time offset  (LDS/STS immediate offsets, no
+// per-access address arithmetic) and free of bank conflicts for the scattered writes and the strided
+// reads at every N and CW (64-bit accesses, half-warp phases; simulated offline).
+template <int CW> struct Skew {
+    static constexpr bool ON = (CW < 16);
+    __host__ __device__ static constexpr int f(int idx) { return ON ? idx + (idx >> 4) : idx; }
+};
+// float2 words of one exchange buffer holding CW interleaved transforms of length N
+template <int N, int CW> __host__ __device__ constexpr int ex_words() { return Skew<CW>::f(N) * CW; }
+
+// Barrier policies of the exchanges: the whole CTA, or a named barrier shared by one group of
+// `threads` threads (several independent groups per CTA, col_tma.cu's pipelined kernel).
+struct CtaBarrier {
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct GroupBarrier {
+    int id, threads;
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 };
 
 // One Stockham stage of radix R with sub-transform length NS already done.
@@ -180,9 +200,10 @@ template <int N, int R, int NS> __device__ __forceinline__ void stage_butterflie
 #pragma unroll
         for (int r = 0; r < R; ++r) x[r] = v[b + r * NB];
         if constexpr (NS > 1) {
-            const float2* twb = tw + TwOffset<N, NS>::value + b * (R - 1) * T + t;
+            using St = TwStage<N, NS>;
+            const float2* twb = tw + TwOffset<N, NS>::value + (St::SHARED_B ? (t & (NS - 1)) : b * (R - 1) * T + t);
 #pragma unroll
-            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(twb + (r - 1) * T));
+            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(twb + (r - 1) * St::PER_R));
         }
         Dft<R>::run(x);
 #pragma unroll
@@ -193,38 +214,44 @@ template <int N, int R, int NS> __device__ __forceinline__ void stage_butterflie
 // Scatter the stage outputs to shared memory and gather the next stage's inputs.
 // ex: this CTA's exchange buffer (N*CW float2); c = transform index in the tile.
 // LEAD_SYNC = false when the caller guarantees nobody still reads `ex` (double-buffered exchanges).
-template <int N, int CW, int R, int NS, bool LEAD_SYNC = true> __device__ __forceinline__ void stage_exchange(float2* v, float2* ex, int t, int c) {
+template <int N, int CW, int R, int NS, bool LEAD_SYNC = true, class Bar = CtaBarrier>
+__device__ __forceinline__ void stage_exchange(float2* v, float2* ex, int t, int c, const Bar& bar = Bar()) {
     constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T, NB = E / R;
-    char* exb = reinterpret_cast<char*>(ex);
-    if constexpr (LEAD_SYNC) __syncthreads();
+    static_assert(NS == 1 || NS % 16 == 0, "stage offsets must not carry into the skew term");
+    if constexpr (LEAD_SYNC) bar.sync();
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int j = t + b * T;
-        const int base = ((j & ~(NS - 1)) * R) + (j & (NS - 1));
-        const int a0 = (Swz<CW>::f(base) * CW + c) * 8;
+        const int base = ((j & ~(NS - 1)) * R) + (j & (NS - 1));  // NS == 1: a multiple of 16 (R == 16), or N < 32
+        float2* w0 = ex + Skew<CW>::f(base) * CW + c;
 #pragma unroll
-        for (int q = 0; q < R; ++q) *reinterpret_cast<float2*>(exb + (a0 ^ (Swz<CW>::f(q * NS) * CW * 8))) = v[b + q * NB];
+        for (int q = 0; q < R; ++q) w0[((NS == 1) ? q : Skew<CW>::f(q * NS)) * CW] = v[b + q * NB];
     }
-    __syncthreads();
-    const int r0 = (Swz<CW>::f(t) * CW + c) * 8;
+    bar.sync();
+    if constexpr (T % 16 == 0) {
+        const float2* r0 = ex + Skew<CW>::f(t) * CW + c;
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = *reinterpret_cast<const float2*>(exb + (r0 ^ (Swz<CW>::f(T * m) * CW * 8)));
+        for (int m = 0; m < E; ++m) v[m] = r0[Skew<CW>::f(T * m) * CW];
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = ex[Skew<CW>::f(t + T * m) * CW + c];
+    }
 }
 
 // DB = true: `ex` holds TWO exchange buffers of N*CW float2 used alternately, which removes the
 // write-after-read barrier of every exchange (one __syncthreads per exchange instead of two).
 template <int N, int CW, int NS, bool DB = false, int XI = 0> struct FftStages {
-    __device__ __forceinline__ static void run(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c) {
+    template <class Bar> __device__ __forceinline__ static void run(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c, const Bar& bar) {
         constexpr int E = FftGeom<N>::E;
         constexpr int REM = N / NS;
         constexpr int R = (REM < E) ? REM : E;
         stage_butterflies<N, R, NS>(v, tw, t);
         if constexpr (NS * R < N) {
             if constexpr (DB)
-                stage_exchange<N, CW, R, NS, false>(v, ex + (size_t)(XI & 1) * N * CW, t, c);
+                stage_exchange<N, CW, R, NS, false>(v, ex + (size_t)(XI & 1) * ex_words<N, CW>(), t, c, bar);
             else
-                stage_exchange<N, CW, R, NS, true>(v, ex, t, c);
-            FftStages<N, CW, NS * R, DB, XI + 1>::run(v, ex, tw, t, c);
+                stage_exchange<N, CW, R, NS, true>(v, ex, t, c, bar);
+            FftStages<N, CW, NS * R, DB, XI + 1>::run(v, ex, tw, t, c, bar);
         }
     }
 };
@@ -232,22 +259,23 @@ template <int N, int CW, int NS, bool DB = false, int XI = 0> struct FftStages {
 // Forward FFT of length N over the E points held by thread t (points t + T*m).
 // All T*CW threads of all transforms in the CTA must call this together when N > E
 // (it contains __syncthreads).
-template <int N, int CW, bool DB = false> __device__ __forceinline__ void fft_forward(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c) {
-    if constexpr (N > 1) FftStages<N, CW, 1, DB>::run(v, ex, tw, t, c);
+template <int N, int CW, bool DB = false, class Bar = CtaBarrier>
+__device__ __forceinline__ void fft_forward(float2* v, float2* ex, const float2* __restrict__ tw, int t, int c, const Bar& bar = Bar()) {
+    if constexpr (N > 1) FftStages<N, CW, 1, DB>::run(v, ex, tw, t, c, bar);
 }
 
 // Shared memory (bytes) one CTA needs for `ntransforms` interleaved transforms of length N.
-template <int N> constexpr size_t fft_smem_bytes(int ntransforms) {
-    return (N > FftGeom<N>::E) ? (size_t)N * ntransforms * sizeof(float2) : 0;
+template <int N, int CW> constexpr size_t fft_smem_bytes() {
+    return (N > FftGeom<N>::E) ? (size_t)ex_words<N, CW>() * sizeof(float2) : 0;
 }
 
 // Fills the twiddle table of length N (TwTotal<N>::value entries), double precision.
 template <int N, int NS> __device__ __forceinline__ void tw_fill_stage(float2* tw, int i) {
     using St = TwStage<N, NS>;
-    constexpr int T = St::T, R = St::R;
+    constexpr int T = St::T, R = St::R, PER_R = St::PER_R;
     if constexpr (NS > 1) {
         if (i < St::ENTRIES) {
-            const int t = i % T, rr = (i / T) % (R - 1), b = i / (T * (R - 1));
+            const int t = i % PER_R, rr = (i / PER_R) % (R - 1), b = i / (PER_R * (R - 1));
             const int k = (t + b * T) & (NS - 1);
             double s, c;
             sincospi(2.0 * (double)((rr + 1) * k) / (double)(NS * R), &s, &c);

@@ -52,19 +52,30 @@ cudaError_t launch_motion_psf(float* psf, int size, PsfAffine m, cudaStream_t s)
 // min/max bookkeeping.  Pass 3 keeps per-plane extrema as order-preserving uints.
 // ---------------------------------------------------------------------------------
 __global__ void minmax_reset_kernel(unsigned int* mm, int units) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < units) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one (unit, slot) entry each
+    if (i < units * FDR_MINMAX_SLOTS) {
         mm[2 * i] = 0xFFFFFFFFu;
         mm[2 * i + 1] = 0u;
     }
 }
 cudaError_t launch_minmax_reset(unsigned int* minmax, int units, cudaStream_t s) {
-    minmax_reset_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax, units);
+    minmax_reset_kernel<<<(units * FDR_MINMAX_SLOTS + 127) / 128, 128, 0, s>>>(minmax, units);
     return cudaGetLastError();
 }
 
 __device__ __forceinline__ float f32_from_ordered(unsigned int u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+// fold the FDR_MINMAX_SLOTS slots of plane i
+__device__ __forceinline__ void minmax_fold(const unsigned int* mm, int i, unsigned int& lo, unsigned int& hi) {
+    lo = 0xFFFFFFFFu;
+    hi = 0u;
+    const uint2* e = reinterpret_cast<const uint2*>(mm) + (size_t)i * FDR_MINMAX_SLOTS;
+    for (int k = 0; k < FDR_MINMAX_SLOTS; ++k) {
+        const uint2 v = e[k];
+        lo = min(lo, v.x);
+        hi = max(hi, v.y);
+    }
 }
 
 // cv::normalize(NORM_MINMAX, 0, 1) (fft_serial.cpp:246) as OpenCV 4.x evaluates it for a CV_32F
@@ -73,8 +84,10 @@ __device__ __forceinline__ float f32_from_ordered(unsigned int u) {
 __global__ void minmax_finalize_kernel(const unsigned int* mm, float2* ss, float* mmf, int units) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= units) return;
-    const double smin = (double)f32_from_ordered(mm[2 * i]);
-    const double smax = (double)f32_from_ordered(mm[2 * i + 1]);
+    unsigned int lo, hi;
+    minmax_fold(mm, i, lo, hi);
+    const double smin = (double)f32_from_ordered(lo);
+    const double smax = (double)f32_from_ordered(hi);
     const double scale = (smax - smin) > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0;
     const float a = (float)scale;
     const float b = 0.0f - (float)__dmul_rn(smin, (double)a);
@@ -86,10 +99,14 @@ __global__ void minmax_finalize_kernel(const unsigned int* mm, float2* ss, float
 }
 __global__ void minmax_decode_kernel(const unsigned int* mm, float* mmf, int units) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 2 * units) mmf[i] = f32_from_ordered(mm[i]);
+    if (i >= units) return;
+    unsigned int lo, hi;
+    minmax_fold(mm, i, lo, hi);
+    mmf[2 * i] = f32_from_ordered(lo);
+    mmf[2 * i + 1] = f32_from_ordered(hi);
 }
 cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, cudaStream_t s) {
-    minmax_decode_kernel<<<(2 * units + 127) / 128, 128, 0, s>>>(minmax, minmax_f32, units);
+    minmax_decode_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax, minmax_f32, units);
     return cudaGetLastError();
 }
 

@@ -17,6 +17,8 @@
 
 namespace fdr {
 
+constexpr int FDR_MINMAX_SLOTS = 128;  // atomic slots per plane for the min/max of pass 3
+
 // ROW_IN_GATHER / ROW_OUT_SCATTER are the row-sharded (multi-GPU) forms: the row lives on this
 // GPU, its columns are spread over `world` column slabs [rows_padded][n/world], one per GPU, reached
 // through peer-mapped pointers (NVLink).  The transpose of the reference's MPI_Alltoallv
@@ -50,7 +52,9 @@ struct RowPassArgs {
     float* raw;                  // local unit u at raw + u*raw_unit_stride, cropped rows x cols
     long long raw_unit_stride;
     int raw_rows, raw_cols;      // H, W : only y < H, x < W is stored
-    unsigned int* minmax;        // [local unit][2] ordered-uint encoded min, max over the PADDED plane
+    unsigned int* minmax;        // [local unit][FDR_MINMAX_SLOTS][2] ordered-uint encoded min, max over the PADDED plane;
+                                 // CTAs spread their atomics over the slots (same-address atomics from every CTA of a
+                                 // plane cost pass 3 up to 70 %, profiles/ubench), the finalize/decode kernels fold them
     int local_units;             // units in this chunk
     // ---- row-sharded exchange (ROW_IN_GATHER / ROW_OUT_SCATTER) ----
     float2* const* peers;        // device array [world]: base of every GPU's column slab (NULL = skip that peer)
@@ -73,7 +77,8 @@ struct ColPassArgs {
     const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
     float2* wiener_out;   // COL_MAKE_WIENER
     float K;
-    int plain_loads;      // COL_WIENER: 1 = force the plain-load kernel instead of the TMA one (timing probe)
+    int col_variant;      // COL_WIENER kernel choice (timing probe): 0 = default dispatch, 1 = plain-load kernel,
+                          // 2 = TMA kernel, one tile per CTA, 3 = TMA kernel, persistent + pipelined (col_tma.cu)
 };
 
 // Launchers (defined in passes_*.cu).  Return cudaGetLastError() of the launch.

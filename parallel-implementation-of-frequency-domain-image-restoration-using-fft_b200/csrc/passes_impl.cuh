@@ -32,7 +32,8 @@ template <int LOGN> struct RowGeom {
     static constexpr int MIN_BLOCKS = (THREADS == 128 && N >= 1024) ? 9 : 1;
     // double-buffered exchange (one barrier per exchange) while two buffers of all rows fit 32 KB
     static constexpr bool DB = false;  // measured slower on B200: the second buffer costs one resident CTA per SM
-    static constexpr size_t SMEM = fft_smem_bytes<N>(RPC) * (DB ? 2 : 1);
+    static constexpr int EXW = ex_words<N, 1>();  // float2 words of one row's exchange buffer
+    static constexpr size_t SMEM = fft_smem_bytes<N, 1>() * RPC * (DB ? 2 : 1);
 };
 
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLO
     const int row = blockIdx.x * RPC + rl;
     const int pair = blockIdx.y + a.pair_base;
     const bool active = row < a.nrows;
-    float2* ex = smem2 + (size_t)rl * N * (Gm::DB ? 2 : 1);
+    float2* ex = smem2 + (size_t)rl * Gm::EXW * (Gm::DB ? 2 : 1);
 
     const long long u0 = 2LL * pair, u1 = u0 + 1;  // local units
     const bool has1 = (a.unit_base + u1) < a.units_total;
@@ -219,11 +220,14 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLO
                 mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
             }
             if (lane == 0) {
-                atomicMin(a.minmax + 2 * u0, f32_ordered(mn0));
-                atomicMax(a.minmax + 2 * u0 + 1, f32_ordered(mx0));
+                const int slot = blockIdx.x & (FDR_MINMAX_SLOTS - 1);
+                unsigned int* m0 = a.minmax + (u0 * FDR_MINMAX_SLOTS + slot) * 2;
+                atomicMin(m0, f32_ordered(mn0));
+                atomicMax(m0 + 1, f32_ordered(mx0));
                 if (has1) {
-                    atomicMin(a.minmax + 2 * u1, f32_ordered(mn1));
-                    atomicMax(a.minmax + 2 * u1 + 1, f32_ordered(mx1));
+                    unsigned int* m1 = a.minmax + (u1 * FDR_MINMAX_SLOTS + slot) * 2;
+                    atomicMin(m1, f32_ordered(mn1));
+                    atomicMax(m1 + 1, f32_ordered(mx1));
                 }
             }
         }
@@ -245,7 +249,7 @@ template <int LOGN, int CW> struct ColGeom {
     static constexpr int E = FftGeom<N>::E;
     static constexpr int T = FftGeom<N>::T;
     static constexpr int THREADS = T * CW;
-    static constexpr size_t SMEM = fft_smem_bytes<N>(CW);
+    static constexpr size_t SMEM = fft_smem_bytes<N, CW>();
 };
 
 template <int LOGN, int CW, int MODE, bool CONJ>

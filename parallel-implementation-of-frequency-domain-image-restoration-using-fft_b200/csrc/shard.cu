@@ -42,7 +42,7 @@ struct fdr_shard {
     DevBuf<float2> slab;      // [npairs][Rp][Cl]
     DevBuf<float2> wiener;    // [Rp][Cl]
     DevBuf<float> raw;        // [C][rows_local][W]
-    DevBuf<unsigned int> mm;  // [C][2] ordered
+    DevBuf<unsigned int> mm;  // [C][FDR_MINMAX_SLOTS][2] ordered
     DevBuf<float> mmf;        // [C][2] floats: min, max (all-reduced by the caller)
     DevBuf<float2> ss;        // [C] scale, shift
     DevBuf<float> psf;
@@ -146,7 +146,7 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
     if (rc == FDR_OK) rc = s->slab.ensure((size_t)s->npairs * Rp * s->Cl);
     if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Cl);
     if (rc == FDR_OK) rc = s->raw.ensure((size_t)channels * (s->rows_local > 0 ? s->rows_local : 1) * cols);
-    if (rc == FDR_OK) rc = s->mm.ensure((size_t)channels * 2);
+    if (rc == FDR_OK) rc = s->mm.ensure((size_t)channels * 2 * FDR_MINMAX_SLOTS);
     if (rc == FDR_OK) rc = s->mmf.ensure((size_t)channels * 2);
     if (rc == FDR_OK) rc = s->ss.ensure((size_t)channels);
     if (rc == FDR_OK) rc = s->peers.ensure((size_t)world);
@@ -281,7 +281,7 @@ FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int p
         const int u0 = 2 * pair_first;
         int nu = 2 * pair_count;
         if (u0 + nu > s->C) nu = s->C - u0;
-        FDR_CUDA(launch_minmax_reset(s->mm.p + 2 * u0, nu, st));
+        FDR_CUDA(launch_minmax_reset(s->mm.p + (size_t)2 * FDR_MINMAX_SLOTS * u0, nu, st));
         s->launches += 1;
     }
     if (s->rows_local == 0) return FDR_OK;  // slab entirely inside the zero padding
@@ -378,7 +378,7 @@ FDR_API int fdr_shard_phase3_pairs(fdr_shard* s, int pair_first, int pair_count,
         const int u0 = 2 * pair_first;
         int nu = 2 * pair_count;
         if (u0 + nu > s->C) nu = s->C - u0;
-        FDR_CUDA(launch_minmax_decode(s->mm.p + 2 * u0, s->mmf.p + 2 * u0, nu, st));
+        FDR_CUDA(launch_minmax_decode(s->mm.p + (size_t)2 * FDR_MINMAX_SLOTS * u0, s->mmf.p + 2 * u0, nu, st));
     }
     s->launches += 2;
     return FDR_OK;
