@@ -62,6 +62,7 @@ struct fdr_plan {
     DevBuf<double> wb_sums;       // chunk images x 2 (Lab white balance)
     int white_balance = 0;        // 8-bit outputs go through the Lab white-balance stage (gpu.cpp:123-134)
     DevBuf<float2> wiener;        // Rp x Cp (digit-swapped row order when col_split is set)
+    DevBuf<float2> wiener_tiled;  // tile-major copy for the wide column kernel (Rp == 2048), passes.h
     DevBuf<float2> wiener_nat;    // natural-order copy, built lazily for the parity-gate API of long-column plans
     bool col_split = false;       // long columns: four-step column pass (col_split.cuh)
     DevBuf<float> psf;            // psf_rows x psf_cols
@@ -257,6 +258,7 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         c2.data = spec_l;
         c2.cplane = (long long)p->plane_elems();
         c2.wiener = p->wiener.p;
+        c2.wiener_tiled = p->wiener_tiled.p;
         c2.K = p->K;
         c2.tw = p->tw_cols;
         {
@@ -385,6 +387,18 @@ struct ScopedTimer {  // event pair on a stream, accumulating into a bucket (Pro
 int build_wiener(fdr_plan* p) {
     p->wiener_nat.release();
     FDR_TRY(build_wiener_into(p, p->wiener, p->col_split));
+    p->wiener_tiled.release();
+    {
+        ColPassArgs probe{};
+        probe.n = p->Rp;
+        probe.pitch = p->Cp;
+        probe.mode = COL_WIENER;
+        if (!p->col_split && col_wide_applicable(probe)) {
+            FDR_TRY(p->wiener_tiled.ensure(p->plane_elems()));
+            FDR_CUDA(launch_wiener_retile(p->wiener.p, p->wiener_tiled.p, p->Rp, p->Cp, p->stream));
+            FDR_CUDA(cudaStreamSynchronize(p->stream));
+        }
+    }
     p->have_wiener = true;
     return FDR_OK;
 }
@@ -498,6 +512,7 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
     p->wb_sums.release();
     p->wiener.release();
     p->wiener_nat.release();
+    p->wiener_tiled.release();
     p->psf.release();
     p->d_in_u8.release();
     p->d_out_u8.release();
@@ -792,7 +807,9 @@ __attribute__((visibility("default"))) int fdr_plan_get_kernel_timing(fdr_plan* 
 // Timing probe: runs one pass `reps` times on a workspace of `npairs` plane pairs and returns the
 // mean device time.  pass: 1 = rows forward (u8 in), 2 = columns, 3 = rows inverse + min/max.
 // variant (pass 2): 0 = Wiener, default dispatch; 1 = Wiener, plain-load kernel; 2 = one forward FFT;
-// 3 = load + store only; 4 = Wiener, TMA kernel with one tile per CTA; 5 = Wiener, persistent pipelined TMA kernel.
+// 3 = load + store only; 4 = Wiener, TMA kernel with one tile per CTA; 5 = Wiener, persistent pipelined TMA kernel;
+// 6 = Wiener, TMA kernel on the 64-points-per-thread core; 7 / 8 = its transfer-only probes (2 / 3 tile transfers, no FFT);
+// 9 = the wide core in the persistent pipelined form.
 __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int pass, int variant, int npairs, int reps, float* ms_avg) {
     if (!p || !ms_avg || npairs < 1 || reps < 1) return set_error(FDR_E_INVALID, "bad arguments");
     if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
@@ -810,8 +827,9 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     ColPassArgs c2{};
     c2.n = p->Rp; c2.pitch = p->Cp; c2.npairs = npairs; c2.rows_valid = p->H; c2.data = p->spec.p;
     c2.cplane = (long long)p->plane_elems(); c2.wiener = p->wiener.p; c2.K = p->K; c2.tw = p->tw_cols;
+    c2.wiener_tiled = getenv("FDR_NO_WIENER_TILED") ? nullptr : p->wiener_tiled.p;
     c2.mode = variant == 2 ? COL_FFT : variant == 3 ? COL_COPY : COL_WIENER;
-    c2.col_variant = (variant == 1) ? 1 : (variant == 4) ? 2 : (variant == 5) ? 3 : 0;
+    c2.col_variant = (variant == 1) ? 1 : (variant == 4) ? 2 : (variant == 5) ? 3 : (variant == 6) ? 4 : (variant == 7) ? 5 : (variant == 8) ? 6 : (variant == 9) ? 7 : 0;
     RowPassArgs r3{};
     r3.n = p->Cp; r3.nrows = p->Rp; r3.npairs = npairs; r3.in_mode = ROW_IN_COMPLEX; r3.out_mode = ROW_OUT_REAL_PAIR;
     r3.cin = p->spec.p; r3.cplane = (long long)p->plane_elems(); r3.units_total = nu; r3.raw = p->raw.p;
@@ -821,6 +839,7 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     FDR_CUDA(launch_minmax_reset(p->mm.p, nu, s));
     auto run = [&]() -> cudaError_t {
         if (pass == 1) return launch_row_pass(r1, s);
+        if (pass == 2 && variant >= 100) return launch_tma_copy_probe(c2, variant - 100, s);  // 100 + box columns
         if (pass == 2) return (p->col_split && c2.mode == COL_WIENER) ? launch_col_split(c2, s, nullptr) : launch_col_pass(c2, s);
         return launch_row_pass(r3, s);
     };

@@ -10,46 +10,12 @@
 //   load tile (TMA) -> registers -> FFT -> Wiener tile (TMA into the now idle exchange buffer) ->
 //   multiply, conj -> FFT -> registers -> shared -> store tile (TMA)
 // One 64 KB buffer per CTA serves as TMA landing zone, exchange buffer and TMA source; 2 CTAs/SM.
-#include <cuda.h>
-
 #include <cstdlib>
 
 #include "passes_impl.cuh"
+#include "tma_util.cuh"
 
 namespace fdr {
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int x, int y, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int x, int y, const void* smem_src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(x), "r"(y),
-                 "r"(smem_u32(smem_src))
-                 : "memory");
-}
 
 template <int LOGN, int CW>
 __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>::THREADS <= 512) ? 1024 / ColGeom<LOGN, CW>::THREADS : 1)
@@ -243,35 +209,6 @@ __global__ void __launch_bounds__(ColPipeGeom<LOGN, CW>::THREADS, 1)
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// rows x cols complex plane(s), row-major: 2-D tensor of 32-bit floats [rows][2*cols], box = box_rows x (2*cw)
-static bool make_map(CUtensorMap* tm, const void* base, long long rows, int cols, int cw, int box_rows) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 8};
-    cuuint32_t box[2] = {(cuuint32_t)cw * 2, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 bool col_tma_applicable(const ColPassArgs& a) {
     static int enabled = -1;
     if (enabled < 0) {
@@ -283,15 +220,15 @@ bool col_tma_applicable(const ColPassArgs& a) {
     const int cw = col_pass_tile_width(a.n);  // (the 1024 case falls back to this width when 4 does not divide the pitch)
     if (a.pitch % cw != 0 || a.cplane != (long long)a.n * a.pitch) return false;
     if ((reinterpret_cast<uintptr_t>(a.data) & 15) || (reinterpret_cast<uintptr_t>(a.wiener) & 15)) return false;
-    return get_encode() != nullptr;
+    return tma_get_encode() != nullptr;
 }
 
 template <int LOGN, int CW = default_col_cw(LOGN)> static cudaError_t launch_t(const ColPassArgs& a, cudaStream_t s) {
     using Gm = ColGeom<LOGN, CW>;
     constexpr int BOX_ROWS = (Gm::N < 256) ? Gm::N : 256;
     CUtensorMap tm_data, tm_w;
-    if (!make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
-    if (!make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
+    if (!tma_make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
+    if (!tma_make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
     static unsigned long long configured = 0;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -310,8 +247,8 @@ template <int LOGN, int CW = default_col_cw(LOGN)> static cudaError_t launch_pip
     using Pg = ColPipeGeom<LOGN, CW>;
     constexpr int BOX_ROWS = (Gm::N < 256) ? Gm::N : 256;
     CUtensorMap tm_data, tm_w;
-    if (!make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
-    if (!make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
+    if (!tma_make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
+    if (!tma_make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
     static unsigned long long configured = 0;
     static int sms[64];
     int dev = 0;

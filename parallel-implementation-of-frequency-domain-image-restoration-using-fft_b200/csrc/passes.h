@@ -75,10 +75,14 @@ struct ColPassArgs {
     float2* data;         // in place; pair p at data + p*cplane
     long long cplane;
     const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
+    const float2* wiener_tiled;  // optional tile-major copy [pitch/4][n][4] (launch_wiener_retile): each column tile of
+                                 // the wide kernel is then ONE contiguous 64 KB block instead of n 32-byte rows
     float2* wiener_out;   // COL_MAKE_WIENER
     float K;
     int col_variant;      // COL_WIENER kernel choice (timing probe): 0 = default dispatch, 1 = plain-load kernel,
-                          // 2 = TMA kernel, one tile per CTA, 3 = TMA kernel, persistent + pipelined (col_tma.cu)
+                          // 2 = TMA kernel, one tile per CTA, 3 = TMA kernel, persistent + pipelined (col_tma.cu),
+                          // 4 = TMA kernel on the 64-points-per-thread core (col_wide.cu), 5 / 6 = its transfer-only probes,
+                          // 7 = wide core, persistent + pipelined
 };
 
 // Launchers (defined in passes_*.cu).  Return cudaGetLastError() of the launch.
@@ -93,6 +97,14 @@ cudaError_t launch_col_split(const ColPassArgs& a, cudaStream_t s, int* launches
 // COL_WIENER with TMA-staged tiles (col_tma.cu), 256 <= n <= 4096, row-major planes.
 bool col_tma_applicable(const ColPassArgs& a);
 cudaError_t launch_col_wiener_tma(const ColPassArgs& a, cudaStream_t s);
+// COL_WIENER on the 64-points-per-thread core (col_wide.cu), n = 2048; same preconditions as the TMA kernel.
+bool col_wide_applicable(const ColPassArgs& a);
+cudaError_t launch_col_wiener_wide(const ColPassArgs& a, cudaStream_t s);
+// timing probe: copy the workspace through 64 KB shared-memory tiles of box_cols columns with TMA
+cudaError_t launch_tma_copy_probe(const ColPassArgs& a, int box_cols, cudaStream_t s);
+constexpr int WIDE_CW = 4;  // columns per tile of the wide kernel
+// dst[(xt*n + row)*WIDE_CW + c] = src[row*pitch + xt*WIDE_CW + c]
+cudaError_t launch_wiener_retile(const float2* src, float2* dst, int n, int pitch, cudaStream_t s);
 // Tile width (columns per CTA) the column pass uses for length n.
 int col_pass_tile_width(int n);
 

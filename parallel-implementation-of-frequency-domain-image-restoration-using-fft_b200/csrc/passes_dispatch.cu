@@ -33,7 +33,7 @@ cudaError_t launch_row_pass(const RowPassArgs& a, cudaStream_t s) {
 }
 
 cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s) {
-    if (a.col_variant != 1 && col_tma_applicable(a)) return launch_col_wiener_tma(a, s);
+    if (a.col_variant != 1 && col_tma_applicable(a)) return col_wide_applicable(a) ? launch_col_wiener_wide(a, s) : launch_col_wiener_tma(a, s);
     switch (ilog2_exact(a.n)) {
 #define X(LOGN) \
     case LOGN: return launch_col_pass_##LOGN(a, s);
