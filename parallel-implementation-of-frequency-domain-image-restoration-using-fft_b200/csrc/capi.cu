@@ -610,14 +610,18 @@ __attribute__((visibility("default"))) int fdr_plan_get_wiener_host(const fdr_pl
     if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
     FDR_CUDA(cudaSetDevice(p->device));
     if (p->col_split) {
-        // stored with digit-swapped rows: row 128*k1 + k2 holds frequency k1 + (Rp/128)*k2 (layout conversion only)
+        // stored with digit-swapped rows: row M*k1 + k2 holds frequency k1 + (Rp/M)*k2 (layout conversion only)
         std::vector<float2> tmp(p->plane_elems());
         FDR_CUDA(cudaMemcpy(tmp.data(), p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));
         float2* out = reinterpret_cast<float2*>(wf);
-        const int n1 = p->Rp / 128;
+        ColPassArgs probe{};
+        probe.n = p->Rp;
+        probe.pitch = p->Cp;
+        probe.mode = COL_WIENER;
+        const int M = col_split_block_len(probe), n1 = p->Rp / M;
         for (int k1 = 0; k1 < n1; ++k1)
-            for (int k2 = 0; k2 < 128; ++k2)
-                memcpy(out + (size_t)(k1 + n1 * k2) * p->Cp, tmp.data() + (size_t)(128 * k1 + k2) * p->Cp, sizeof(float2) * p->Cp);
+            for (int k2 = 0; k2 < M; ++k2)
+                memcpy(out + (size_t)(k1 + n1 * k2) * p->Cp, tmp.data() + (size_t)(M * k1 + k2) * p->Cp, sizeof(float2) * p->Cp);
         return FDR_OK;
     }
     FDR_CUDA(cudaMemcpy(wf, p->wiener.p, sizeof(float2) * p->plane_elems(), cudaMemcpyDeviceToHost));

@@ -15,7 +15,7 @@ __global__ void tw_full_fill_kernel(float2* tw, int n) {
     tw[i] = make_float2((float)c, (float)(-s));
 }
 
-static cudaError_t get_full_twiddles(int n, const float2** out) {
+cudaError_t get_full_twiddles(int n, const float2** out) {
     static std::mutex mu;
     static std::map<std::pair<int, int>, float2*> cache;
     int dev = 0;
@@ -73,7 +73,10 @@ static cudaError_t launch_block(const ColSplitArgs& s, cudaStream_t st) {
 }
 
 // Whole column pass, panel by panel; *launches receives the number of kernels launched.
+int col_split_block_len(const ColPassArgs& a) { return col_blocks_applicable(a) ? 2048 : SPLIT_N2; }
+
 cudaError_t launch_col_split(const ColPassArgs& a, cudaStream_t st, int* launches) {
+    if (col_blocks_applicable(a)) return launch_col_blocks(a, st, launches);
     const float2* tw_sub1 = nullptr;
     const float2* tw_sub2 = nullptr;
     const float2* tw_full = nullptr;

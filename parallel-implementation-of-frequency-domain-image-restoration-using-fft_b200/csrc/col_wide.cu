@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(ColWideGeom<LOGN, CW>::THREADS, ColWideGeom<LO
     const int x0 = xt * CW * 2;               // tensor maps count 32-bit floats along x
     const int y0 = (pr + a.pair_base) * N;    // pair p occupies tensor rows [p*N, (p+1)*N)
     const int nbox_valid = (a.rows_valid + BOX_ROWS - 1) / BOX_ROWS;
+    const int kb = (a.wiener_blocks > 1) ? (pr + a.pair_base) % a.wiener_blocks : 0;  // row block of the Wiener factor
 
     if (tid == 0) {
         mbar_init(&bar, 1);
@@ -90,10 +91,10 @@ __global__ void __launch_bounds__(ColWideGeom<LOGN, CW>::THREADS, ColWideGeom<LO
         if (tid == 0) {
             mbar_expect_tx(&bar, NBOX * BOX_BYTES);
             if (a.wiener_tiled) {  // one contiguous block per tile
-                const float2* src = a.wiener_tiled + (size_t)xt * N * CW;
+                const float2* src = a.wiener_tiled + ((size_t)kb * (a.pitch / CW) + xt) * N * CW;
                 for (int b = 0; b < NBOX; ++b) bulk_load_1d(ex + (size_t)b * BOX_ROWS * CW, src + (size_t)b * BOX_ROWS * CW, BOX_BYTES, &bar);
             } else {
-                for (int b = 0; b < NBOX; ++b) tma_load_2d(ex + (size_t)b * BOX_ROWS * CW, &tm_w, x0, b * BOX_ROWS, &bar);
+                for (int b = 0; b < NBOX; ++b) tma_load_2d(ex + (size_t)b * BOX_ROWS * CW, &tm_w, x0, kb * N + b * BOX_ROWS, &bar);
             }
         }
     };
@@ -289,7 +290,7 @@ template <int LOGN, int CW, int PROBE = 0> static cudaError_t launch_wide_t(cons
     using Gm = ColWideGeom<LOGN, CW>;
     CUtensorMap tm_data, tm_w;
     if (!tma_make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, 256)) return cudaErrorInvalidValue;
-    if (!tma_make_map(&tm_w, a.wiener, a.n, a.pitch, CW, 256)) return cudaErrorInvalidValue;
+    if (!tma_make_map(&tm_w, a.wiener, (long long)a.n * (a.wiener_blocks > 1 ? a.wiener_blocks : 1), a.pitch, CW, 256)) return cudaErrorInvalidValue;
     const float2* tw = nullptr;
     cudaError_t e = wide_twiddles<Gm::N>(&tw);
     if (e != cudaSuccess) return e;
@@ -402,7 +403,8 @@ cudaError_t launch_col_wiener_wide(const ColPassArgs& a, cudaStream_t s) {
     // measured slower than the per-tile form (8 warps per SM instead of 12: 20.6 vs 17.2 us per pair of 2048^2): opt-in only
     if (pipe_enabled < 0) pipe_enabled = (getenv("FDR_WIDE_PIPE") && atoi(getenv("FDR_WIDE_PIPE")) == 1) ? 1 : 0;
     const long long ntiles = (long long)(a.pitch / WIDE_CW) * a.npairs;
-    if (a.n == 2048 && (a.col_variant == 7 || (a.col_variant == 0 && pipe_enabled && ntiles >= 4 * 148))) return launch_wide_pipe_t<11, 4>(a, s);
+    if (a.n == 2048 && a.wiener_blocks <= 1 && (a.col_variant == 7 || (a.col_variant == 0 && pipe_enabled && ntiles >= 4 * 148)))
+        return launch_wide_pipe_t<11, 4>(a, s);
     switch (a.n) {
         case 2048: return a.col_variant == 5 ? launch_wide_t<11, 4, 1>(a, s) : a.col_variant == 6 ? launch_wide_t<11, 4, 2>(a, s) : launch_wide_t<11, 4>(a, s);
     }

@@ -77,6 +77,8 @@ struct ColPassArgs {
     const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
     const float2* wiener_tiled;  // optional tile-major copy [pitch/4][n][4] (launch_wiener_retile): each column tile of
                                  // the wide kernel is then ONE contiguous 64 KB block instead of n 32-byte rows
+    int wiener_blocks;    // wide kernel: > 1 = the factor is a stack of that many n-row blocks and pair p uses block
+                          // (pair_base + p) % wiener_blocks (the K x 2048 long-column scheme, col_blocks.cu)
     float2* wiener_out;   // COL_MAKE_WIENER
     float K;
     int col_variant;      // COL_WIENER kernel choice (timing probe): 0 = default dispatch, 1 = plain-load kernel,
@@ -90,10 +92,14 @@ cudaError_t launch_row_pass(const RowPassArgs& a, cudaStream_t s);
 cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s);
 // Twiddle table for power-of-two length n on the current device (cached).
 cudaError_t get_twiddles(int n, const float2** out);
-// Long columns (n = 8192, 16384), COL_WIENER / COL_MAKE_WIENER: four-step column pass (col_split.cuh).
-// The Wiener factor it reads/writes is in digit-swapped row order: row 128*k1 + k2 holds frequency k1 + (n/128)*k2.
+// Long columns (n = 8192, 16384), COL_WIENER / COL_MAKE_WIENER: split column pass -- K x 2048 blocks (col_blocks.cu) when the
+// wide TMA kernel applies, else 128 x 128 four-step (col_split.cuh).  The Wiener factor it reads/writes is in digit-swapped row
+// order: row M*k1 + k2 holds frequency k1 + (n/M)*k2 with M = col_split_block_len(args) (2048 or 128).
 bool col_split_applicable(const ColPassArgs& a);
 cudaError_t launch_col_split(const ColPassArgs& a, cudaStream_t s, int* launches);
+int col_split_block_len(const ColPassArgs& a);
+bool col_blocks_applicable(const ColPassArgs& a);
+cudaError_t launch_col_blocks(const ColPassArgs& a, cudaStream_t s, int* launches);
 // COL_WIENER with TMA-staged tiles (col_tma.cu), 256 <= n <= 4096, row-major planes.
 bool col_tma_applicable(const ColPassArgs& a);
 cudaError_t launch_col_wiener_tma(const ColPassArgs& a, cudaStream_t s);
