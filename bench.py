@@ -491,7 +491,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+            per_pair = json.load(open(tp)).get(args.workload, {}).get("per_plane_pair", {}).get(dom)
+            traffic = per_pair * iso_pairs if per_pair else None  # per launch, like `achieved`
         except Exception:
             traffic = None
     ksum = sum(v["ms"] for v in ktimes.values())

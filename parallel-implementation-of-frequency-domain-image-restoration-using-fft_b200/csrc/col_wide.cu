@@ -281,7 +281,8 @@ bool col_wide_applicable(const ColPassArgs& a) {
         const char* env = getenv("FDR_COL_WIDE");
         enabled = (env && atoi(env) == 0) ? 0 : 1;
     }
-    if (a.col_variant >= 4 && a.col_variant <= 7) return a.n == 2048 && a.pitch % 4 == 0;
+    if (a.col_variant == 4) return (a.n == 2048 || a.n == 4096) && a.pitch % 4 == 0;
+    if (a.col_variant >= 5 && a.col_variant <= 7) return a.n == 2048 && a.pitch % 4 == 0;
     if (!enabled || a.col_variant != 0) return false;
     return a.n == 2048 && a.pitch % 4 == 0;
 }
@@ -406,6 +407,7 @@ cudaError_t launch_col_wiener_wide(const ColPassArgs& a, cudaStream_t s) {
     if (a.n == 2048 && a.wiener_blocks <= 1 && (a.col_variant == 7 || (a.col_variant == 0 && pipe_enabled && ntiles >= 4 * 148)))
         return launch_wide_pipe_t<11, 4>(a, s);
     switch (a.n) {
+        case 4096: return launch_wide_t<12, 4>(a, s);
         case 2048: return a.col_variant == 5 ? launch_wide_t<11, 4, 1>(a, s) : a.col_variant == 6 ? launch_wide_t<11, 4, 2>(a, s) : launch_wide_t<11, 4>(a, s);
     }
     return cudaErrorInvalidValue;
