@@ -186,7 +186,7 @@ def run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H
     sh = stream.cuda_stream
     back = fd.cuda_shard_backend(fdr, H, W, 3, rank, world, local_rank)
     drv = fd.ShardedRestorer(back, device=dev)
-    back.set_psf_motion(plen, pang, K_WIENER)
+    drv.set_psf_motion(plen, pang, K_WIENER)  # builds the Wiener slab on every rank, then fences across ranks
     n_rows, first = back.n_rows, back.first_row
     d_in = torch.empty((max(n_rows, 1), W, 3), dtype=torch.uint8, device=dev)
     d_out = torch.empty_like(d_in)

@@ -166,6 +166,8 @@ int fdr_ipc_open(const unsigned char handle[64], void** dptr);
 int fdr_ipc_close(void* dptr);
 /* slabs[world]: every rank's slab as a pointer valid on THIS device (entry `rank` is ignored). */
 int fdr_shard_set_peers(fdr_shard* shard, void* const* slabs);
+/* Both build the rank's slab of the Wiener factor using the rank's COLUMN SLAB as scratch: fence across ranks (all ranks
+ * returned from this call) before the first fdr_shard_phase1 of any rank, which stores into the peers' slabs. */
 int fdr_shard_set_psf_motion(fdr_shard* shard, int length, double angle_deg, float K);
 int fdr_shard_set_psf_host(fdr_shard* shard, const float* psf, int psf_rows, int psf_cols, float K);
 /* d_in_rows_u8 / d_out_rows_u8: this rank's rows, interleaved 8-bit [n_rows][cols][channels]. */

@@ -70,6 +70,21 @@ class ShardedRestorer:
         self._flag = torch.zeros(1, dtype=torch.float32, device=self._mm.device)
         self._side = None                             # side streams + flags of the pair pipeline
 
+    def set_psf_motion(self, length, angle_deg, K):
+        """PSF + Wiener factor on every rank, then a cross-rank fence: the build uses the rank's column slab as
+        scratch, so no peer may start scattering into it (phase 1 of a restore) before every rank is done."""
+        self.b.set_psf_motion(length, angle_deg, K)
+        self._fence()
+
+    def set_psf(self, psf, K):
+        self.b.set_psf(psf, K)
+        self._fence()
+
+    def _fence(self):
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+
     def barrier(self, flag=None):
         """Stream-ordered cross-rank barrier: a 1-element all-reduce on the current stream."""
         if self.world > 1:

@@ -120,8 +120,10 @@ def test_wiener_factor(gpu, oracle):
 
 RESTORE_CASES = [(48, 80, 9, 30.0), (64, 64, 5, 10.0), (100, 200, 21, 45.0), (7, 9, 3, 20.0), (1, 33, 1, 0.0),
                  (33, 1, 1, 0.0), (1, 1, 1, 0.0), (256, 256, 50, 30.0), (330, 640, 40, 45.0), (17, 300, 15, 123.4),
-                 # long columns: four-step column pass (col_split), 8192 = 64*128 and 16384 = 128*128
-                 (8192, 48, 9, 30.0), (5000, 100, 21, 45.0), (16384, 40, 5, 10.0), (9000, 16, 3, 20.0)]
+                 # long columns: K x 2048 blocks (col_blocks.cu) or, for pitches the TMA kernel cannot take, the 128-point four-step (col_split)
+                 (8192, 48, 9, 30.0), (5000, 100, 21, 45.0), (16384, 40, 5, 10.0), (9000, 16, 3, 20.0),
+                 # 2048 padded rows: the 64-points-per-thread column kernel (col_wide.cu), full and zero-padded columns
+                 (2048, 96, 9, 30.0), (1100, 40, 5, 10.0)]
 
 
 @pytest.mark.parametrize("H,W,S,ang", RESTORE_CASES)

@@ -70,11 +70,12 @@ def test_sharded_equals_single_gpu_and_oracle(gpu, oracle, H, W, world):
     assert worse == 0 and (exact + off1) / got.size >= 0.999
 
 
-def test_sharded_per_pair_phases(gpu, oracle):
-    """fdr_shard_phase*_pairs: running the two plane pairs separately (as the pipelined driver does)
-    gives the same bytes as the all-pairs phases."""
+@pytest.mark.parametrize("H,W,world", [(192, 256, 2), (8192, 64, 2), (16384, 4096, 2)])
+def test_sharded_per_pair_phases(gpu, oracle, H, W, world):
+    """fdr_shard_phase*_pairs: running the two plane pairs separately, on two concurrent streams (as
+    the pipelined driver does), gives the same bytes as the all-pairs phases -- also for the long-column
+    schemes (8192 / 16384 rows) at a realistic slab width."""
     torch = pytest.importorskip("torch")
-    H, W, world = 192, 256, 2
     img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 1, H, W), (1, 2, 0)))
     want, _ = run_emulated(gpu, torch, img, world, 9, 30.0)
     dev = torch.device("cuda", 0)
@@ -89,17 +90,18 @@ def test_sharded_per_pair_phases(gpu, oracle):
             s.set_peers(slabs)
             s.set_psf_motion(9, 30.0, K)
         st = torch.cuda.Stream(device=dev)
+        sts = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
         rb = W * 3
         for ph in (1, 2, 3):
-            for pair in (1, 0):  # order between pairs must not matter
+            for pair in (1, 0):  # order between pairs must not matter; the two pairs run concurrently
                 for s in shards:
                     if ph == 1:
-                        s.phase1(d_in.data_ptr() + s.first_row * rb, st.cuda_stream, pair=pair)
+                        s.phase1(d_in.data_ptr() + s.first_row * rb, sts[pair].cuda_stream, pair=pair)
                     elif ph == 2:
-                        s.phase2(st.cuda_stream, pair=pair)
+                        s.phase2(sts[pair].cuda_stream, pair=pair)
                     else:
-                        s.phase3(st.cuda_stream, pair=pair)
-                torch.cuda.synchronize()
+                        s.phase3(sts[pair].cuda_stream, pair=pair)
+            torch.cuda.synchronize()
         mms = [dist_mod.device_tensor(s.minmax_ptr(), (3, 2), dev) for s in shards]
         allmm = torch.stack(mms)
         gmin, gmax = allmm[:, :, 0].min(0).values, allmm[:, :, 1].max(0).values
