@@ -813,7 +813,7 @@ __attribute__((visibility("default"))) int fdr_plan_get_kernel_timing(fdr_plan* 
 // variant (pass 2): 0 = Wiener, default dispatch; 1 = Wiener, plain-load kernel; 2 = one forward FFT;
 // 3 = load + store only; 4 = Wiener, TMA kernel with one tile per CTA; 5 = Wiener, persistent pipelined TMA kernel;
 // 6 = Wiener, TMA kernel on the 64-points-per-thread core; 7 / 8 = its transfer-only probes (2 / 3 tile transfers, no FFT);
-// 9 = the wide core in the persistent pipelined form.
+// 9 = the wide core in the persistent pipelined form; 10 = wide core at 4096 with 4-column tiles (one CTA per SM).
 __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int pass, int variant, int npairs, int reps, float* ms_avg) {
     if (!p || !ms_avg || npairs < 1 || reps < 1) return set_error(FDR_E_INVALID, "bad arguments");
     if (!p->have_wiener) return set_error(FDR_E_STATE, "no PSF set");
@@ -833,7 +833,7 @@ __attribute__((visibility("default"))) int fdr_plan_time_pass(fdr_plan* p, int p
     c2.cplane = (long long)p->plane_elems(); c2.wiener = p->wiener.p; c2.K = p->K; c2.tw = p->tw_cols;
     c2.wiener_tiled = getenv("FDR_NO_WIENER_TILED") ? nullptr : p->wiener_tiled.p;
     c2.mode = variant == 2 ? COL_FFT : variant == 3 ? COL_COPY : COL_WIENER;
-    c2.col_variant = (variant == 1) ? 1 : (variant == 4) ? 2 : (variant == 5) ? 3 : (variant == 6) ? 4 : (variant == 7) ? 5 : (variant == 8) ? 6 : (variant == 9) ? 7 : 0;
+    c2.col_variant = (variant == 1) ? 1 : (variant == 4) ? 2 : (variant == 5) ? 3 : (variant == 6) ? 4 : (variant == 7) ? 5 : (variant == 8) ? 6 : (variant == 9) ? 7 : (variant == 10) ? 8 : 0;
     RowPassArgs r3{};
     r3.n = p->Cp; r3.nrows = p->Rp; r3.npairs = npairs; r3.in_mode = ROW_IN_COMPLEX; r3.out_mode = ROW_OUT_REAL_PAIR;
     r3.cin = p->spec.p; r3.cplane = (long long)p->plane_elems(); r3.units_total = nu; r3.raw = p->raw.p;

@@ -281,10 +281,10 @@ bool col_wide_applicable(const ColPassArgs& a) {
         const char* env = getenv("FDR_COL_WIDE");
         enabled = (env && atoi(env) == 0) ? 0 : 1;
     }
-    if (a.col_variant == 4) return (a.n == 2048 || a.n == 4096) && a.pitch % 4 == 0;
+    if (a.col_variant == 4 || a.col_variant == 8) return (a.n == 2048 || a.n == 4096) && a.pitch % 4 == 0;
     if (a.col_variant >= 5 && a.col_variant <= 7) return a.n == 2048 && a.pitch % 4 == 0;
     if (!enabled || a.col_variant != 0) return false;
-    return a.n == 2048 && a.pitch % 4 == 0;
+    return (a.n == 2048 || a.n == 4096) && a.pitch % 4 == 0;
 }
 
 template <int LOGN, int CW, int PROBE = 0> static cudaError_t launch_wide_t(const ColPassArgs& a, cudaStream_t s) {
@@ -357,19 +357,19 @@ cudaError_t launch_tma_copy_probe(const ColPassArgs& a, int box_cols, cudaStream
     return cudaErrorInvalidValue;
 }
 
-static_assert(WIDE_CW == 4, "the 2048-point wide kernel is instantiated for 4-column tiles");
-
-__global__ void wiener_retile_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int n, int pitch) {
+__global__ void wiener_retile_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int n, int pitch, int cw) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index into dst
     if (i >= (long long)n * pitch) return;
-    const int c = (int)(i % WIDE_CW);
-    const long long q = i / WIDE_CW;
+    const int c = (int)(i % cw);
+    const long long q = i / cw;
     const int row = (int)(q % n), xt = (int)(q / n);
-    dst[i] = src[(long long)row * pitch + xt * WIDE_CW + c];
+    dst[i] = src[(long long)row * pitch + xt * cw + c];
 }
 cudaError_t launch_wiener_retile(const float2* src, float2* dst, int n, int pitch, cudaStream_t s) {
+    const int cw = wide_tile_cols(n);
+    if (cw == 0 || pitch % cw != 0) return cudaErrorInvalidValue;
     const long long total = (long long)n * pitch;
-    wiener_retile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, n, pitch);
+    wiener_retile_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, dst, n, pitch, cw);
     return cudaGetLastError();
 }
 
@@ -403,11 +403,11 @@ cudaError_t launch_col_wiener_wide(const ColPassArgs& a, cudaStream_t s) {
     static int pipe_enabled = -1;
     // measured slower than the per-tile form (8 warps per SM instead of 12: 20.6 vs 17.2 us per pair of 2048^2): opt-in only
     if (pipe_enabled < 0) pipe_enabled = (getenv("FDR_WIDE_PIPE") && atoi(getenv("FDR_WIDE_PIPE")) == 1) ? 1 : 0;
-    const long long ntiles = (long long)(a.pitch / WIDE_CW) * a.npairs;
+    const long long ntiles = (long long)(a.pitch / 4) * a.npairs;
     if (a.n == 2048 && a.wiener_blocks <= 1 && (a.col_variant == 7 || (a.col_variant == 0 && pipe_enabled && ntiles >= 4 * 148)))
         return launch_wide_pipe_t<11, 4>(a, s);
     switch (a.n) {
-        case 4096: return launch_wide_t<12, 4>(a, s);
+        case 4096: return a.col_variant == 8 ? launch_wide_t<12, 4>(a, s) : launch_wide_t<12, 2>(a, s);
         case 2048: return a.col_variant == 5 ? launch_wide_t<11, 4, 1>(a, s) : a.col_variant == 6 ? launch_wide_t<11, 4, 2>(a, s) : launch_wide_t<11, 4>(a, s);
     }
     return cudaErrorInvalidValue;

@@ -75,8 +75,8 @@ struct ColPassArgs {
     float2* data;         // in place; pair p at data + p*cplane
     long long cplane;
     const float2* wiener; // COL_WIENER: Wf, row-major n x pitch
-    const float2* wiener_tiled;  // optional tile-major copy [pitch/4][n][4] (launch_wiener_retile): each column tile of
-                                 // the wide kernel is then ONE contiguous 64 KB block instead of n 32-byte rows
+    const float2* wiener_tiled;  // optional tile-major copy [pitch/cw][n][cw] (launch_wiener_retile): each column tile of
+                                 // the wide kernel is then ONE contiguous 64 KB block instead of n short rows
     int wiener_blocks;    // wide kernel: > 1 = the factor is a stack of that many n-row blocks and pair p uses block
                           // (pair_base + p) % wiener_blocks (the K x 2048 long-column scheme, col_blocks.cu)
     float2* wiener_out;   // COL_MAKE_WIENER
@@ -108,8 +108,9 @@ bool col_wide_applicable(const ColPassArgs& a);
 cudaError_t launch_col_wiener_wide(const ColPassArgs& a, cudaStream_t s);
 // timing probe: copy the workspace through 64 KB shared-memory tiles of box_cols columns with TMA
 cudaError_t launch_tma_copy_probe(const ColPassArgs& a, int box_cols, cudaStream_t s);
-constexpr int WIDE_CW = 4;  // columns per tile of the wide kernel
-// dst[(xt*n + row)*WIDE_CW + c] = src[row*pitch + xt*WIDE_CW + c]
+// columns per tile of the wide kernel for length n (64 KB tiles): 4 at 2048, 2 at 4096; 0 = length not served
+constexpr int wide_tile_cols(int n) { return n == 2048 ? 4 : n == 4096 ? 2 : 0; }
+// tile-major copy of the Wiener factor: dst[(xt*n + row)*cw + c] = src[row*pitch + xt*cw + c], cw = wide_tile_cols(n)
 cudaError_t launch_wiener_retile(const float2* src, float2* dst, int n, int pitch, cudaStream_t s);
 // Tile width (columns per CTA) the column pass uses for length n.
 int col_pass_tile_width(int n);
