@@ -281,10 +281,13 @@ bool col_wide_applicable(const ColPassArgs& a) {
         const char* env = getenv("FDR_COL_WIDE");
         enabled = (env && atoi(env) == 0) ? 0 : 1;
     }
-    if (a.col_variant == 4 || a.col_variant == 8) return (a.n == 2048 || a.n == 4096) && a.pitch % 4 == 0;
-    if (a.col_variant >= 5 && a.col_variant <= 7) return a.n == 2048 && a.pitch % 4 == 0;
+    const bool geom = wide_tile_cols(a.n) > 0 && a.pitch % (wide_tile_cols(a.n) < 4 ? 4 : wide_tile_cols(a.n)) == 0;
+    if (a.col_variant == 4) return geom;
+    if (a.col_variant == 8) return a.n == 4096 && geom;
+    if (a.col_variant >= 5 && a.col_variant <= 7) return a.n == 2048 && geom;
     if (!enabled || a.col_variant != 0) return false;
-    return (a.n == 2048 || a.n == 4096) && a.pitch % 4 == 0;
+    // 1024: 4.96 vs 5.15 us per pair in large batches but a worse wave fit for single images (cat: 0.096 vs 0.093 ms): opt-in only
+    return geom && a.n != 1024;
 }
 
 template <int LOGN, int CW, int PROBE = 0> static cudaError_t launch_wide_t(const ColPassArgs& a, cudaStream_t s) {
@@ -407,6 +410,7 @@ cudaError_t launch_col_wiener_wide(const ColPassArgs& a, cudaStream_t s) {
     if (a.n == 2048 && a.wiener_blocks <= 1 && (a.col_variant == 7 || (a.col_variant == 0 && pipe_enabled && ntiles >= 4 * 148)))
         return launch_wide_pipe_t<11, 4>(a, s);
     switch (a.n) {
+        case 1024: return launch_wide_t<10, 8>(a, s);
         case 4096: return a.col_variant == 8 ? launch_wide_t<12, 4>(a, s) : launch_wide_t<12, 2>(a, s);
         case 2048: return a.col_variant == 5 ? launch_wide_t<11, 4, 1>(a, s) : a.col_variant == 6 ? launch_wide_t<11, 4, 2>(a, s) : launch_wide_t<11, 4>(a, s);
     }

@@ -108,8 +108,8 @@ bool col_wide_applicable(const ColPassArgs& a);
 cudaError_t launch_col_wiener_wide(const ColPassArgs& a, cudaStream_t s);
 // timing probe: copy the workspace through 64 KB shared-memory tiles of box_cols columns with TMA
 cudaError_t launch_tma_copy_probe(const ColPassArgs& a, int box_cols, cudaStream_t s);
-// columns per tile of the wide kernel for length n (64 KB tiles): 4 at 2048, 2 at 4096; 0 = length not served
-constexpr int wide_tile_cols(int n) { return n == 2048 ? 4 : n == 4096 ? 2 : 0; }
+// columns per tile of the wide kernel for length n (64 KB tiles): 8 at 1024, 4 at 2048, 2 at 4096; 0 = length not served
+constexpr int wide_tile_cols(int n) { return n == 1024 ? 8 : n == 2048 ? 4 : n == 4096 ? 2 : 0; }
 // tile-major copy of the Wiener factor: dst[(xt*n + row)*cw + c] = src[row*pitch + xt*cw + c], cw = wide_tile_cols(n)
 cudaError_t launch_wiener_retile(const float2* src, float2* dst, int n, int pitch, cudaStream_t s);
 // Tile width (columns per CTA) the column pass uses for length n.
