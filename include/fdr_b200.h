@@ -114,8 +114,11 @@ int fdr_plan_set_kernel_timing(fdr_plan* plan, int enabled);
 int fdr_plan_get_kernel_timing(fdr_plan* plan, double total_ms[4], long long launches[4], double bytes[4]);
 /* Timing probe for kernel work: runs one pass `reps` times back to back on a synthetic workspace
  * of `npairs` plane pairs and returns the mean device time in ms.  pass 1 = rows forward,
- * 2 = columns (variant 0 = Wiener default (TMA tiles), 1 = Wiener with plain loads, 2 = single forward FFT,
- * 3 = load+store only), 3 = rows inverse + min/max. */
+ * 2 = columns, 3 = rows inverse + min/max.  Column variants: 0 = Wiener, default dispatch; 1 = Wiener with plain
+ * loads; 2 = single forward FFT; 3 = load+store only; 4 / 5 = 16-point TMA kernel, one tile per CTA / persistent
+ * pipelined; 6 = 64-point (wide) TMA kernel; 7 / 8 = its transfer-only probes (2 / 3 tile transfers, no FFT);
+ * 9 = wide kernel, persistent pipelined; 10 = wide kernel at 4096 rows with 4-column tiles; 100 + w = TMA copy of
+ * 64 KB tiles w columns wide, in and out (what the box width costs).  Probes leave garbage in the workspace. */
 int fdr_plan_time_pass(fdr_plan* plan, int pass, int variant, int npairs, int reps, float* ms_avg);
 /* Number of kernels the most recent restore call launched. */
 int fdr_plan_last_launch_count(const fdr_plan* plan, long long* launches);
