@@ -92,7 +92,7 @@ struct fdr_plan {
     std::vector<cudaEvent_t> ev_pool;
 
     size_t plane_elems() const { return (size_t)Rp * Cp; }
-    // Images per device chunk.  Measured on B200 (profiles/r1/chunk_sweep.txt): the passes are bound by the
+    // Images per device chunk.  Measured on B200 (profiles/r1b/chunk_sweep_small.txt): the passes are bound by the
     // SM-side load/store pipe or by HBM, not helped by L2 residency between passes, and every launch pays
     // a partial last wave -- so large chunks win: 32 images of 2048^2 (1.5 GB of spectrum) run 12 % faster
     // than the 96 MB chunks that fit the L2.  An even unit count per chunk keeps plane pairs inside a chunk.
