@@ -61,6 +61,7 @@ struct RowPassArgs {
     int peer_shift;              // log2(n / world): column x belongs to peer x >> peer_shift
     long long peer_plane;        // elements per pair in a slab = rows_padded * (n / world)
     int row0;                    // global (padded) index of local row 0
+    int max_ctas;                // > 0: scatter / gather passes run as at most this many persistent CTAs per pair
 };
 
 struct ColPassArgs {

@@ -36,15 +36,17 @@ template <int LOGN> struct RowGeom {
     static constexpr size_t SMEM = fft_smem_bytes<N, 1>() * RPC * (DB ? 2 : 1);
 };
 
+// One block of RPC rows of pair blockIdx.y; `row_block` is blockIdx.x in the one-shot kernel and the loop
+// index in the persistent one.
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
-__global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLOCKS) row_pass_kernel(const RowPassArgs a) {
+__device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int row_block) {
     using Gm = RowGeom<LOGN>;
     constexpr int N = Gm::N, E = Gm::E, T = Gm::T, RPC = Gm::RPC;
     extern __shared__ float2 smem2[];
     const int tid = threadIdx.x;
     const int rl = (RPC > 1) ? (tid / T) : 0;
     const int t = (RPC > 1) ? (tid % T) : tid;
-    const int row = blockIdx.x * RPC + rl;
+    const int row = row_block * RPC + rl;
     const int pair = blockIdx.y + a.pair_base;
     const bool active = row < a.nrows;
     float2* ex = smem2 + (size_t)rl * Gm::EXW * (Gm::DB ? 2 : 1);
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLO
                 mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
             }
             if (lane == 0) {
-                const int slot = blockIdx.x & (FDR_MINMAX_SLOTS - 1);
+                const int slot = row_block & (FDR_MINMAX_SLOTS - 1);
                 unsigned int* m0 = a.minmax + (u0 * FDR_MINMAX_SLOTS + slot) * 2;
                 atomicMin(m0, f32_ordered(mn0));
                 atomicMax(m0 + 1, f32_ordered(mx0));
@@ -231,6 +233,23 @@ __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLO
                 }
             }
         }
+    }
+}
+
+template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
+__global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLOCKS) row_pass_kernel(const RowPassArgs a) {
+    row_pass_body<LOGN, IN_MODE, OUT_MODE, CONJ>(a, blockIdx.x);
+}
+
+// Grid-limited persistent form (a.max_ctas CTAs per pair, each looping over row blocks): the NVLink-bound
+// exchange passes of the row-sharded path then leave SMs free for the other plane pair's column phase
+// (fdr_dist pair pipeline).  Only instantiated for the scatter / gather modes.
+template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
+__global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLOCKS) row_pass_persist_kernel(const RowPassArgs a) {
+    const int nblk = (a.nrows + RowGeom<LOGN>::RPC - 1) / RowGeom<LOGN>::RPC;
+    for (int rb = blockIdx.x; rb < nblk; rb += gridDim.x) {
+        row_pass_body<LOGN, IN_MODE, OUT_MODE, CONJ>(a, rb);
+        __syncthreads();  // shared memory (exchange buffer, min/max scratch) is reused by the next block
     }
 }
 
@@ -332,6 +351,24 @@ template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row
         }
     }
     dim3 grid((a.nrows + Gm::RPC - 1) / Gm::RPC, a.npairs);
+    if constexpr (IN_MODE == ROW_IN_GATHER || OUT_MODE == ROW_OUT_SCATTER) {
+        if (a.max_ctas > 0 && (unsigned)a.max_ctas < grid.x) {
+            if (Gm::SMEM > 48 * 1024) {
+                static unsigned long long configured_p = 0;
+                int dev = 0;
+                cudaGetDevice(&dev);
+                if (!(configured_p >> (dev & 63) & 1ULL)) {
+                    cudaError_t e = cudaFuncSetAttribute(row_pass_persist_kernel<LOGN, IN_MODE, OUT_MODE, CONJ>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+                    if (e != cudaSuccess) return e;
+                    configured_p |= 1ULL << (dev & 63);
+                }
+            }
+            grid.x = a.max_ctas;
+            row_pass_persist_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
+            return cudaGetLastError();
+        }
+    }
     row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
     return cudaGetLastError();
 }

@@ -58,6 +58,17 @@ struct fdr_shard {
 namespace {
 cudaStream_t pick(fdr_shard* s, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : s->stream; }
 
+// FDR_SHARD_ROW_CTAS=n: the exchange passes (phase 1 scatter, phase 3 gather) run as at most n persistent CTAs per
+// plane pair, leaving the other SMs to the other pair's column phase in the pair-pipelined driver.  0 = whole grid.
+int shard_row_ctas() {
+    static int v = -1;
+    if (v < 0) {
+        const char* env = getenv("FDR_SHARD_ROW_CTAS");
+        v = (env && atoi(env) > 0) ? atoi(env) : 0;
+    }
+    return v;
+}
+
 int build_wiener(fdr_shard* s) {
     if (s->psf_rows > s->Rp || s->psf_cols > s->Cp)
         return set_error(FDR_E_INVALID, "PSF %dx%d larger than the padded image %dx%d", s->psf_rows, s->psf_cols, s->Rp, s->Cp);
@@ -304,6 +315,7 @@ FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int p
     r.peer_shift = ilog2(s->Cl);
     r.peer_plane = (long long)s->Rp * s->Cl;
     r.row0 = s->row0;
+    r.max_ctas = shard_row_ctas();
     FDR_CUDA(launch_row_pass(r, st));
     s->launches += 1;
     return FDR_OK;
@@ -373,6 +385,7 @@ FDR_API int fdr_shard_phase3_pairs(fdr_shard* s, int pair_first, int pair_count,
     r.peer_shift = ilog2(s->Cl);
     r.peer_plane = (long long)s->Rp * s->Cl;
     r.row0 = s->row0;
+    r.max_ctas = shard_row_ctas();
     FDR_CUDA(launch_row_pass(r, st));
     {
         const int u0 = 2 * pair_first;
