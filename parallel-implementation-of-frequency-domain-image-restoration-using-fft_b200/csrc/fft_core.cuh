@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace fdr {
 
 // Blackwell (sm_100) packed fp32x2 arithmetic: one FADD2 per complex add/subtract.  The kernels are
@@ -130,6 +132,49 @@ template <> struct Dft<16> {
     }
 };
 
+// ---- compile-time roots of unity (constant twiddles inside the wide radices and derived table twiddles) ----
+__host__ __device__ constexpr double wide_sin(double x) {  // Taylor series, |x| <= 2 pi, compile time only
+    double term = x, sum = x;
+    for (int i = 1; i < 32; ++i) {
+        term *= -x * x / ((2 * i) * (2 * i + 1));
+        sum += term;
+    }
+    return sum;
+}
+__host__ __device__ constexpr double wide_cos(double x) {
+    double term = 1.0, sum = 1.0;
+    for (int i = 1; i < 32; ++i) {
+        term *= -x * x / ((2 * i - 1) * (2 * i));
+        sum += term;
+    }
+    return sum;
+}
+
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// a * exp(-2 pi i J / M) with compile-time J, M
+template <int M, int J> __device__ __forceinline__ float2 cmul_root(float2 a) {
+    constexpr int j = ((J % M) + M) % M;
+    if constexpr (j == 0)
+        return a;
+    else if constexpr (4 * j == M)
+        return make_float2(a.y, -a.x);
+    else if constexpr (2 * j == M)
+        return make_float2(-a.x, -a.y);
+    else if constexpr (4 * j == 3 * M)
+        return make_float2(-a.y, a.x);
+    else {
+        constexpr double ang = 6.283185307179586476925286766559 * j / M;
+        constexpr float wr = (float)wide_cos(ang), wi = (float)(-wide_sin(ang));
+        return cmulc(a, wr, wi);
+    }
+}
+
 template <int N> struct FftGeom {
     static constexpr int E = (N >= 16) ? 16 : N;  // points per thread
     static constexpr int T = N / E;               // threads per transform
@@ -139,8 +184,10 @@ template <int N> struct FftGeom {
 // Twiddle table of one length N: for every stage after the first and every r = 1..R-1 the factors
 // exp(-2 pi i * r * k / (NS*R)), k = (t + b*T) mod NS.  While NS <= T the index k = t mod NS does not
 // depend on the butterfly b and only NS distinct entries exist per r (layout [r][k]: the two half-warps
-// of a load coincide, one 128-byte wavefront); for NS > T the layout is [b][r][t].  Offsets are
-// compile-time.
+// of a load coincide, one 128-byte wavefront).  For NS > T (always the last stage) only butterfly 0 is
+// tabulated ([r][t]); butterfly b uses the same entries times the compile-time constant W_E^{r b}
+// (k = t + b T and NS R = N, so exp(-2 pi i r b T / N) = W_16^{r b}): a few FP instructions instead of a
+// second set of loads on the L1 data pipe, which is what bounds pass 1.  Offsets are compile-time.
 // ---------------------------------------------------------------------------------
 template <int N, int NS> struct TwStage {
     static constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T;
@@ -149,7 +196,7 @@ template <int N, int NS> struct TwStage {
     static constexpr int NB = E / R;
     static constexpr bool SHARED_B = (NS <= T);          // k independent of b
     static constexpr int PER_R = SHARED_B ? NS : T;      // entries per (b, r)
-    static constexpr int ENTRIES = (NS > 1) ? (SHARED_B ? 1 : NB) * (R - 1) * PER_R : 0;
+    static constexpr int ENTRIES = (NS > 1) ? (R - 1) * PER_R : 0;
     // table offset of this stage = entries of all earlier stages
 };
 // All stages before the last have radix 16 (greedy radices), so the stage with sub-length NS is
@@ -194,21 +241,30 @@ struct GroupBarrier {
 // One Stockham stage of radix R with sub-transform length NS already done.
 template <int N, int R, int NS> __device__ __forceinline__ void stage_butterflies(float2* v, const float2* __restrict__ tw, int t) {
     constexpr int E = FftGeom<N>::E, T = FftGeom<N>::T, NB = E / R;
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
+    static_for<0, NB>([&](auto bc) {
+        constexpr int b = decltype(bc)::value;
         float2 x[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) x[r] = v[b + r * NB];
         if constexpr (NS > 1) {
             using St = TwStage<N, NS>;
-            const float2* twb = tw + TwOffset<N, NS>::value + (St::SHARED_B ? (t & (NS - 1)) : b * (R - 1) * T + t);
+            const float2* twb = tw + TwOffset<N, NS>::value + (St::SHARED_B ? (t & (NS - 1)) : t);
+            if constexpr (St::SHARED_B || b == 0) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(twb + (r - 1) * St::PER_R));
+                for (int r = 1; r < R; ++r) x[r] = cmul(x[r], __ldg(twb + (r - 1) * St::PER_R));
+            } else {
+                static_assert(b == 0 || (NS * R) % T == 0, "derived twiddles need an integral root order");
+                constexpr int Q = (b == 0) ? 1 : NS * R / T;  // W_Q^{r b} = exp(-2 pi i r b T / (NS R))
+                static_for<1, R>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    x[r] = cmul(cmul_root<Q, r * b>(x[r]), __ldg(twb + (r - 1) * St::PER_R));
+                });
+            }
         }
         Dft<R>::run(x);
 #pragma unroll
         for (int r = 0; r < R; ++r) v[b + r * NB] = x[r];
-    }
+    });
 }
 
 // Scatter the stage outputs to shared memory and gather the next stage's inputs.
@@ -272,11 +328,11 @@ template <int N, int CW> constexpr size_t fft_smem_bytes() {
 // Fills the twiddle table of length N (TwTotal<N>::value entries), double precision.
 template <int N, int NS> __device__ __forceinline__ void tw_fill_stage(float2* tw, int i) {
     using St = TwStage<N, NS>;
-    constexpr int T = St::T, R = St::R, PER_R = St::PER_R;
+    constexpr int R = St::R, PER_R = St::PER_R;
     if constexpr (NS > 1) {
         if (i < St::ENTRIES) {
-            const int t = i % PER_R, rr = (i / PER_R) % (R - 1), b = i / (PER_R * (R - 1));
-            const int k = (t + b * T) & (NS - 1);
+            const int t = i % PER_R, rr = i / PER_R;  // butterfly 0 only (header comment)
+            const int k = t & (NS - 1);
             double s, c;
             sincospi(2.0 * (double)((rr + 1) * k) / (double)(NS * R), &s, &c);
             tw[TwOffset<N, NS>::value + i] = make_float2((float)c, (float)(-s));

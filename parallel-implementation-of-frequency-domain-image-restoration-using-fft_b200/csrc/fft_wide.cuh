@@ -16,53 +16,9 @@
 //
 // Replaces (does not port) /root/reference/fft/fft_gpu.cu:108-148.
 #pragma once
-#include <type_traits>
-
 #include "fft_core.cuh"
 
 namespace fdr {
-
-__host__ __device__ constexpr double wide_sin(double x) {  // Taylor series, |x| <= 2 pi, compile time only
-    double term = x, sum = x;
-    for (int i = 1; i < 32; ++i) {
-        term *= -x * x / ((2 * i) * (2 * i + 1));
-        sum += term;
-    }
-    return sum;
-}
-__host__ __device__ constexpr double wide_cos(double x) {
-    double term = 1.0, sum = 1.0;
-    for (int i = 1; i < 32; ++i) {
-        term *= -x * x / ((2 * i - 1) * (2 * i));
-        sum += term;
-    }
-    return sum;
-}
-
-template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
-
-// a * exp(-2 pi i J / M) with compile-time J, M
-template <int M, int J> __device__ __forceinline__ float2 cmul_root(float2 a) {
-    constexpr int j = ((J % M) + M) % M;
-    if constexpr (j == 0)
-        return a;
-    else if constexpr (4 * j == M)
-        return make_float2(a.y, -a.x);
-    else if constexpr (2 * j == M)
-        return make_float2(-a.x, -a.y);
-    else if constexpr (4 * j == 3 * M)
-        return make_float2(-a.y, a.x);
-    else {
-        constexpr double ang = 6.283185307179586476925286766559 * j / M;
-        constexpr float wr = (float)wide_cos(ang), wi = (float)(-wide_sin(ang));
-        return cmulc(a, wr, wi);
-    }
-}
 
 // Forward DFT of R = R1 * R2 points in registers, natural order in and out:
 // n = R2*n1 + n2, k = k1 + R1*k2; DFT_R1 over n1, twiddle W_R^{n2 k1}, DFT_R2 over n2.
