@@ -82,7 +82,8 @@ class ShardedRestorer:
 
     def _fence(self):
         if self.world > 1:
-            torch.cuda.synchronize()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
             dist.barrier(group=self.group)
 
     def barrier(self, flag=None):

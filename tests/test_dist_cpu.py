@@ -40,7 +40,7 @@ class NumpyShard:
     """Test double with the fdr.Shard phase API.  Slabs live in a shared-memory file per rank so the
     'peer stores/loads' of the kernels become plain numpy indexing into the peers' slabs."""
 
-    def __init__(self, d, tmp, rows, cols, channels, rank, world, psf, K):
+    def __init__(self, d, tmp, rows, cols, channels, rank, world, psf=None, K=0.01):
         self.rank, self.world, self.C = rank, world, channels
         self.H, self.W = rows, cols
         self.Rp, self.Cp = d.next_pow2(rows), d.next_pow2(cols)
@@ -51,11 +51,26 @@ class NumpyShard:
         self.slab = np.memmap(self.path, dtype=np.complex128, mode="w+", shape=(self.npairs, self.Rp, self.Cl))
         self.slab[:] = 0  # rows >= H are never written by anyone; zero BEFORE the handle exchange (a barrier),
         self.slab.flush()  # never inside phase 1, where a faster peer may already be storing its rows here
+        self.mm = torch.zeros((channels, 2), dtype=torch.float64)
+        if psf is not None:
+            self.set_psf(psf, K)
+
+    def set_psf(self, psf, K):
+        """Like fdr_shard_set_psf_*: the Wiener slab is built THROUGH the column slab (pair 0 is the scratch of
+        the PSF's row spectrum), so a peer that scattered into this slab before the build finished would corrupt it."""
         hp = np.zeros((self.Rp, self.Cp))
         hp[: psf.shape[0], : psf.shape[1]] = psf
-        Hs = np.fft.fft2(hp)
-        self.wf = (np.conj(Hs) / (np.abs(Hs) ** 2 + K))[:, rank * self.Cl:(rank + 1) * self.Cl]
-        self.mm = torch.zeros((channels, 2), dtype=torch.float64)
+        cols = slice(self.rank * self.Cl, (self.rank + 1) * self.Cl)
+        slab = np.memmap(self.path, dtype=np.complex128, mode="r+", shape=(self.npairs, self.Rp, self.Cl))
+        slab[0] = np.fft.fft(hp, axis=1)[:, cols]
+        slab.flush()
+        import time
+        time.sleep(0.3 * self.rank)  # skew: rank 0 is done long before the last rank
+        slab = np.memmap(self.path, dtype=np.complex128, mode="r+", shape=(self.npairs, self.Rp, self.Cl))
+        Hs = np.fft.fft(np.array(slab[0]), axis=0)
+        self.wf = np.conj(Hs) / (np.abs(Hs) ** 2 + K)
+        slab[0] = 0
+        slab.flush()
 
     def export_handle(self):
         return self.path
@@ -118,8 +133,9 @@ def _worker(rank, world, port, tmp, H, W, C, result_path):
     img = rng.integers(0, 256, (H, W, C), dtype=np.uint8)
     psf = np.zeros((5, 5))
     psf[2, :] = 0.2
-    back = NumpyShard(d, tmp, H, W, C, rank, world, psf, 0.01)
+    back = NumpyShard(d, tmp, H, W, C, rank, world)
     drv = d.ShardedRestorer(back)
+    drv.set_psf(psf, 0.01)  # fenced: without the cross-rank barrier rank 0's phase 1 lands in rank 1's scratch
     first, n = d.row_slab(rank, world, H)
     out = np.zeros((n, W, C), np.uint8)
     drv.restore_rows(img[first:first + n], out)
