@@ -9,8 +9,9 @@
 //       row 2048*n1 + n2: natural order, what the monolithic COL_WIENER kernel leaves behind.
 // Replaces the 128 x 128 four-step pass (col_split.cu) as the default for these lengths: the same 56 B per
 // complex pixel of traffic, but S1/S3 stream at HBM speed and S2 is the kernel that already runs 2048-row
-// planes at 0.83 of the HBM roofline; col_split's three kernels ran at 1.4 TB/s-equivalent.
+// planes at 0.87-0.89 of the HBM roofline; col_split's three kernels ran at 1.4 TB/s-equivalent.
 // The reference has no counterpart (its shared-memory kernel stops at N = 4096, fft_gpu.cu:219-221).
+#include <cstdint>
 #include <cstdlib>
 
 #include "fft_core.cuh"
@@ -64,8 +65,6 @@ template <int K, bool PRE> static cudaError_t launch_radixk(const ColPassArgs& a
     return cudaGetLastError();
 }
 
-int col_blocks_block_len() { return BLK_M; }
-
 bool col_blocks_applicable(const ColPassArgs& a) {
     static int enabled = -1;
     if (enabled < 0) {
@@ -76,14 +75,12 @@ bool col_blocks_applicable(const ColPassArgs& a) {
     if (a.n != 8192 && a.n != 16384) return false;
     if (a.mode != COL_WIENER && a.mode != COL_MAKE_WIENER) return false;
     if (a.conj || a.pitch % 4 != 0) return false;
-    ColPassArgs sub = a;
+    // every 2048-row block must be a legal plane of the wide TMA kernel (pointer alignment is checked at launch)
+    ColPassArgs sub{};
     sub.n = BLK_M;
+    sub.pitch = a.pitch;
     sub.mode = COL_WIENER;
-    sub.cplane = (long long)BLK_M * a.pitch;
-    sub.col_variant = 0;
-    if (!sub.data) sub.data = reinterpret_cast<float2*>(16);  // geometry probe: alignment is checked at launch time
-    if (!sub.wiener) sub.wiener = reinterpret_cast<const float2*>(16);
-    return col_tma_applicable(sub) && col_wide_applicable(sub);
+    return col_tma_geometry_ok(BLK_M, a.pitch, (long long)BLK_M * a.pitch) && col_wide_applicable(sub);
 }
 
 cudaError_t launch_col_blocks(const ColPassArgs& a, cudaStream_t s, int* launches) {
@@ -92,6 +89,8 @@ cudaError_t launch_col_blocks(const ColPassArgs& a, cudaStream_t s, int* launche
     cudaError_t e = get_full_twiddles(a.n, &tw_full);
     if (e != cudaSuccess) return e;
     if (a.cplane != (long long)a.n * a.pitch) return cudaErrorInvalidValue;
+    if (reinterpret_cast<uintptr_t>(a.data) & 15) return cudaErrorInvalidValue;  // TMA tiles and float4 rows
+    if (a.mode == COL_WIENER && (reinterpret_cast<uintptr_t>(a.wiener) & 15)) return cudaErrorInvalidValue;
     int count = 0;
     // S1
     e = (K == 8) ? launch_radixk<8, false>(a, a.rows_valid, tw_full, s) : launch_radixk<4, false>(a, a.rows_valid, tw_full, s);

@@ -209,18 +209,24 @@ __global__ void __launch_bounds__(ColPipeGeom<LOGN, CW>::THREADS, 1)
     }
 }
 
-bool col_tma_applicable(const ColPassArgs& a) {
+// geometry only (no pointers): can a COL_WIENER pass of length n over planes of this pitch use the TMA kernels?
+bool col_tma_geometry_ok(int n, int pitch, long long cplane) {
     static int enabled = -1;
     if (enabled < 0) {
         const char* env = getenv("FDR_COL_TMA");
         enabled = (env && atoi(env) == 0) ? 0 : 1;
     }
-    if (!enabled || a.mode != COL_WIENER || a.conj) return false;
-    if (a.n < 256 || a.n > 4096 || (a.n & (a.n - 1))) return false;
-    const int cw = col_pass_tile_width(a.n);  // (the 1024 case falls back to this width when 4 does not divide the pitch)
-    if (a.pitch % cw != 0 || a.cplane != (long long)a.n * a.pitch) return false;
-    if ((reinterpret_cast<uintptr_t>(a.data) & 15) || (reinterpret_cast<uintptr_t>(a.wiener) & 15)) return false;
+    if (!enabled) return false;
+    if (n < 256 || n > 4096 || (n & (n - 1))) return false;
+    const int cw = col_pass_tile_width(n);  // (the 1024 case falls back to this width when 4 does not divide the pitch)
+    if (pitch % cw != 0 || cplane != (long long)n * pitch) return false;
     return tma_get_encode() != nullptr;
+}
+
+bool col_tma_applicable(const ColPassArgs& a) {
+    if (a.mode != COL_WIENER || a.conj) return false;
+    if (!col_tma_geometry_ok(a.n, a.pitch, a.cplane)) return false;
+    return !((reinterpret_cast<uintptr_t>(a.data) & 15) || (reinterpret_cast<uintptr_t>(a.wiener) & 15));
 }
 
 template <int LOGN, int CW = default_col_cw(LOGN)> static cudaError_t launch_t(const ColPassArgs& a, cudaStream_t s) {

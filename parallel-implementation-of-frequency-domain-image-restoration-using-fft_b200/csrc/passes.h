@@ -103,6 +103,7 @@ bool col_blocks_applicable(const ColPassArgs& a);
 cudaError_t launch_col_blocks(const ColPassArgs& a, cudaStream_t s, int* launches);
 // COL_WIENER with TMA-staged tiles (col_tma.cu), 256 <= n <= 4096, row-major planes.
 bool col_tma_applicable(const ColPassArgs& a);
+bool col_tma_geometry_ok(int n, int pitch, long long cplane);
 cudaError_t launch_col_wiener_tma(const ColPassArgs& a, cudaStream_t s);
 // COL_WIENER on the 64-points-per-thread core (col_wide.cu), n = 2048; same preconditions as the TMA kernel.
 bool col_wide_applicable(const ColPassArgs& a);
