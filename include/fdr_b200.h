@@ -17,7 +17,12 @@
  *     zero-pad, FFT, G*conj(H)/(|H|^2+K), unscaled inverse FFT, real part, min-max normalise
  *     over the PADDED plane, crop, and for the 8-bit entry points rint(255*x) saturated;
  *   - there is no CPU fallback: without a CUDA device every compute call fails with
- *     FDR_E_CUDA.
+ *     FDR_E_CUDA;
+ *   - streams: a plan owns ONE workspace.  Device entry points are asynchronous on the stream the
+ *     caller passes; calls on different streams (and fdr_plan_set_psf_*, which rebuilds the Wiener
+ *     factor on the plan's own stream) are ordered one after the other through an event, so they are
+ *     safe but never concurrent.  Use one plan per stream for concurrency.  A NULL stream means the
+ *     plan's own non-blocking stream, not the legacy default stream.
  */
 #ifndef FDR_B200_H
 #define FDR_B200_H
@@ -58,6 +63,11 @@ int fdr_plan_padded_size(const fdr_plan* plan, int* padded_rows, int* padded_col
  * BGR -> Lab, L scaled by mean(L_original)/(mean(L_restored)+1e-6) and clamped (applyWhiteBalance,
  * utils.hpp:55-71), Lab -> BGR, convertTo(CV_8U, 255).  Off by default (direct x255 pack). */
 int fdr_plan_set_white_balance(fdr_plan* plan, int enabled);
+/* enabled = 1 when a chunk with an odd plane count (one BGR image, a greyscale image) sends its last plane through the
+ * half-plane path: two rows of that plane per complex row transform, Hermitian half spectrum, half the column work --
+ * instead of a half-empty complex pair (the reference transforms every channel as a full complex plane,
+ * fft_gpu.cu:325-368).  Geometry-dependent; FDR_HALF=0 / FDR_HALF_MIN_PIXELS=<padded pixels> override it. */
+int fdr_plan_half_plane(const fdr_plan* plan, int* enabled);
 /* The post stage alone, for callers that hold normalised planes (what fft_gpu::wienerDeblur_RGB_* returns):
  * restored and original planes in B, G, R order, fp32 in [0,1], contiguous rows x cols -> 8-bit BGR image. */
 int fdr_white_balance_pack_host(const float* const* restored_planes, const float* const* original_planes, int rows, int cols,
@@ -184,6 +194,18 @@ int fdr_shard_phase1_pairs(fdr_shard* shard, const void* d_in_rows_u8, int pair_
 int fdr_shard_phase2_pairs(fdr_shard* shard, int pair_first, int pair_count, void* stream);
 int fdr_shard_phase3_pairs(fdr_shard* shard, int pair_first, int pair_count, void* stream);
 int fdr_shard_pair_count(const fdr_shard* shard, int* pairs);
+/* Half-plane mode (default when the geometry allows; FDR_SHARD_HALF=0 disables): every colour plane is its own pipeline
+ * unit -- local rows y and y+D of ONE plane are packed into a complex row transform, untangled, and only columns
+ * 0 .. Cp/2-1 (+ the Nyquist column, kept on rank `plane % world`) travel and go through the column phase: 1.5 instead of
+ * 2 complex planes for a BGR image.  In this mode the "pair" arguments above index planes and fdr_shard_pair_count
+ * returns the channel count.  Replaces the three per-channel calls of mpi.cpp:95-111. */
+int fdr_shard_half_plane(const fdr_shard* shard, int* enabled);
+/* Exchange passes (phase 1, phase 3) as at most `ctas` persistent CTAs per unit (0 = whole grid; default
+ * FDR_SHARD_ROW_CTAS), leaving SMs to another unit's column phase in the pipelined driver. */
+int fdr_shard_set_row_ctas(fdr_shard* shard, int ctas);
+/* enabled: the vector of fdr_shard_minmax_device holds (min, -max) per plane so that ONE all-reduce(MIN) over all of it
+ * folds both extrema; phase 4 undoes the sign.  Default off (column 0 MIN, column 1 MAX). */
+int fdr_shard_set_minmax_negated(fdr_shard* shard, int enabled);
 /* [channels][2] floats (min, max of this rank's part of every padded plane) to all-reduce in
  * place: column 0 with MIN, column 1 with MAX. */
 int fdr_shard_minmax_device(fdr_shard* shard, void** d_minmax_f32);

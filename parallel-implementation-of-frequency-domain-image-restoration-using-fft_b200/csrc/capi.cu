@@ -65,6 +65,19 @@ struct fdr_plan {
     DevBuf<float2> wiener_tiled;  // tile-major copy for the wide column kernel (Rp == 2048), passes.h
     DevBuf<float2> wiener_nat;    // natural-order copy, built lazily for the parity-gate API of long-column plans
     bool col_split = false;       // long columns: four-step column pass (col_split.cuh)
+    // Half-plane path for the odd colour plane of a chunk (passes.h, ROW_*_HALF): its own Wiener factors, built by the same
+    // kernels at half pitch (so their row order is whatever the column launcher of that geometry expects).
+    bool half_ok = false;         // geometry allows it and FDR_HALF != 0
+    bool col_split_half = false;
+    DevBuf<float2> wiener_half;        // Rp x Cp/2: columns 0 .. Cp/2-1
+    DevBuf<float2> wiener_half_tiled;  // tile-major copy when the wide column kernel serves pitch Cp/2
+    DevBuf<float2> wiener_nyq;         // Rp: column Cp/2, natural row order (plain column kernel)
+    cudaStream_t s_half = nullptr;     // the lone plane's passes run beside the pairs' passes
+    cudaEvent_t ev_half_fork = nullptr, ev_half_join = nullptr;
+    // one workspace per plan: calls on different streams are ordered through this event (include/fdr_b200.h, "Streams")
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
     DevBuf<float> psf;            // psf_rows x psf_cols
     int lanes = 1;                    // chunks in flight on separate streams (FDR_LANES=1..4); with large chunks one is best
     cudaStream_t lane_stream[4] = {};
@@ -108,7 +121,17 @@ struct fdr_plan {
         }
         if ((ci * C) % 2 && ci < n_images_total) ci += 1;
         if (ci > n_images_total) ci = n_images_total;
+        ci = cap_grid(ci);
         return ci < 1 ? 1 : ci;
+    }
+    // plane pairs, planes and images of a chunk index gridDim.y of the pass kernels: stay below 65535 (huge batches of tiny images)
+    int cap_grid(int ci) const {
+        const int max_images = 65534 / (C > 0 ? C : 1);
+        if (ci > max_images) {
+            ci = max_images;
+            if ((ci * C) % 2) ci -= 1;
+        }
+        return ci;
     }
     // Images per chunk of the pipelined HOST entry point: that path is PCIe-bound, so small chunks
     // (about 75 MB of 8-bit input: 6 images of 2048^2) keep the fill and drain of the
@@ -124,6 +147,7 @@ struct fdr_plan {
         }
         if ((ci * C) % 2 && ci < n_images_total) ci += 1;
         if (ci > n_images_total) ci = n_images_total;
+        ci = cap_grid(ci);
         return ci < 1 ? 1 : ci;
     }
 };
@@ -203,6 +227,7 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
     if (!out_u8 && (chunk_units % 2) && chunk_units < n_units) chunk_units += 1;
     FDR_TRY(ensure_workspace(p, (int)chunk_units));
     p->launches = 0;
+    if (p->have_last && p->last_stream != s) FDR_CUDA(cudaStreamWaitEvent(s, p->ev_last, 0));  // the workspace is shared
     const long long HW = (long long)p->H * p->W;
     const int L = (n_units > chunk_units) ? p->lanes : 1;  // several chunks in flight on separate streams
     cudaStream_t s_caller = s;
@@ -224,78 +249,188 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         float* const mmf_l = p->mmf.p + (size_t)lane * p->ws_units * 2;
         p->last_lane = lane;
         FDR_CUDA(launch_minmax_reset(mm_l, nu, s));
-        RowPassArgs r1{};
-        r1.n = p->Cp;
-        r1.nrows = p->H;
-        r1.npairs = np;
-        r1.in_mode = in.mode;
-        r1.out_mode = ROW_OUT_COMPLEX;
-        r1.in_f32 = in.f32;
-        r1.in_unit_stride = in.unit_stride;
-        r1.in_row_stride = in.row_stride;
-        r1.in_u8 = in.u8;
-        r1.channels = C;
-        r1.img_rows = p->H;
-        r1.img_cols = p->W;
-        r1.unit_base = base;
-        r1.units_total = n_units;
-        r1.cout = spec_l;
-        r1.cplane = (long long)p->plane_elems();
-        r1.tw = p->tw_rows;
-        const double px_in = (double)p->H * p->W * (in.mode == ROW_IN_PAIR_U8 ? 1.0 : 4.0) * nu;
+        // An odd plane count leaves one plane without a partner: it takes the half-plane path (passes.h) on a side stream,
+        // beside the pairs, instead of travelling as a half-empty complex pair.
+        const bool lone = (nu & 1) && p->half_ok;
+        const int npf = lone ? nu / 2 : np;  // full pairs
+        const double px_in1 = (double)p->H * p->W * (in.mode == ROW_IN_PAIR_U8 ? 1.0 : 4.0);
         const double P = (double)p->plane_elems();
-        {
-            KernelTimer kt(p, s, 0, px_in + 8.0 * p->H * p->Cp * np);
-            FDR_CUDA(launch_row_pass(r1, s));
+        cudaStream_t sh = s;
+        if (lone && npf > 0) {
+            sh = p->s_half;
+            FDR_CUDA(cudaEventRecord(p->ev_half_fork, s));
+            FDR_CUDA(cudaStreamWaitEvent(sh, p->ev_half_fork, 0));
         }
+        if (npf > 0) {
+            RowPassArgs r1{};
+            r1.n = p->Cp;
+            r1.nrows = p->H;
+            r1.npairs = npf;
+            r1.in_mode = in.mode;
+            r1.out_mode = ROW_OUT_COMPLEX;
+            r1.in_f32 = in.f32;
+            r1.in_unit_stride = in.unit_stride;
+            r1.in_row_stride = in.row_stride;
+            r1.in_u8 = in.u8;
+            r1.channels = C;
+            r1.img_rows = p->H;
+            r1.img_cols = p->W;
+            r1.unit_base = base;
+            r1.units_total = n_units;
+            r1.cout = spec_l;
+            r1.cplane = (long long)p->plane_elems();
+            r1.tw = p->tw_rows;
+            {
+                KernelTimer kt(p, s, 0, px_in1 * (lone ? nu - 1 : nu) + 8.0 * p->H * p->Cp * npf);
+                FDR_CUDA(launch_row_pass(r1, s));
+            }
 
-        ColPassArgs c2{};
-        c2.n = p->Rp;
-        c2.pitch = p->Cp;
-        c2.npairs = np;
-        c2.mode = COL_WIENER;
-        c2.rows_valid = p->H;
-        c2.data = spec_l;
-        c2.cplane = (long long)p->plane_elems();
-        c2.wiener = p->wiener.p;
-        c2.wiener_tiled = p->wiener_tiled.p;
-        c2.K = p->K;
-        c2.tw = p->tw_cols;
-        {
-            KernelTimer kt(p, s, 1, (8.0 * p->H * p->Cp + 16.0 * P) * np);
-            if (p->col_split) {
-                int nl = 0;
-                FDR_CUDA(launch_col_split(c2, s, &nl));
-                p->launches += nl - 1;
-            } else {
-                FDR_CUDA(launch_col_pass(c2, s));
+            ColPassArgs c2{};
+            c2.n = p->Rp;
+            c2.pitch = p->Cp;
+            c2.npairs = npf;
+            c2.mode = COL_WIENER;
+            c2.rows_valid = p->H;
+            c2.data = spec_l;
+            c2.cplane = (long long)p->plane_elems();
+            c2.wiener = p->wiener.p;
+            c2.wiener_tiled = p->wiener_tiled.p;
+            c2.K = p->K;
+            c2.tw = p->tw_cols;
+            {
+                KernelTimer kt(p, s, 1, (8.0 * p->H * p->Cp + 16.0 * P) * npf);
+                if (p->col_split) {
+                    int nl = 0;
+                    FDR_CUDA(launch_col_split(c2, s, &nl));
+                    p->launches += nl - 1;
+                } else {
+                    FDR_CUDA(launch_col_pass(c2, s));
+                }
+            }
+
+            RowPassArgs r3{};
+            r3.n = p->Cp;
+            r3.nrows = p->Rp;
+            r3.npairs = npf;
+            r3.in_mode = ROW_IN_COMPLEX;
+            r3.out_mode = ROW_OUT_REAL_PAIR;
+            r3.cin = spec_l;
+            r3.cplane = (long long)p->plane_elems();
+            r3.unit_base = base;
+            r3.units_total = n_units;
+            r3.raw = raw_l;
+            r3.raw_unit_stride = HW;
+            r3.raw_rows = p->H;
+            r3.raw_cols = p->W;
+            r3.minmax = mm_l;
+            r3.local_units = nu;
+            r3.tw = p->tw_rows;
+            {
+                KernelTimer kt(p, s, 2, 8.0 * P * npf + 4.0 * HW * (lone ? nu - 1 : nu));
+                FDR_CUDA(launch_row_pass(r3, s));
+            }
+            p->launches += 3;
+        }
+        if (lone) {
+            // workspace of the lone plane: the pair slot after the full pairs holds [Rp][Cp/2] + the Nyquist column [Rp]
+            float2* const hbuf = spec_l + (size_t)npf * p->plane_elems();
+            float2* const nyq = hbuf + (size_t)p->Rp * (p->Cp / 2);
+            const int D1 = (p->H + 1) / 2;
+            RowPassArgs h1{};
+            h1.n = p->Cp;
+            h1.nrows = D1;
+            h1.npairs = 1;
+            h1.pair_base = nu - 1;  // half-plane forms index planes
+            h1.in_mode = (in.mode == ROW_IN_PAIR_U8) ? ROW_IN_ROWS2_U8 : ROW_IN_ROWS2_F32;
+            h1.out_mode = ROW_OUT_HALF;
+            h1.in_f32 = in.f32;
+            h1.in_unit_stride = in.unit_stride;
+            h1.in_row_stride = in.row_stride;
+            h1.in_u8 = in.u8;
+            h1.channels = C;
+            h1.img_rows = p->H;
+            h1.img_cols = p->W;
+            h1.unit_base = base;
+            h1.units_total = n_units;
+            h1.tw = p->tw_rows;
+            h1.pair_dist = D1;
+            h1.rows_in = p->H;
+            h1.hp_rows_store = p->H;
+            h1.hp_peers[0] = hbuf;
+            h1.hp_shift = ilog2(p->Cp / 2);
+            h1.hp_plane = 0;
+            h1.nyq_peers[0] = nyq;
+            h1.nyq_world = 1;
+            h1.nyq_plane = 0;
+            {
+                KernelTimer kt(p, sh, 0, px_in1 + 4.0 * p->H * p->Cp);
+                FDR_CUDA(launch_row_pass(h1, sh));
+            }
+            ColPassArgs ch{};
+            ch.n = p->Rp;
+            ch.pitch = p->Cp / 2;
+            ch.npairs = 1;
+            ch.mode = COL_WIENER;
+            ch.rows_valid = p->H;
+            ch.data = hbuf;
+            ch.cplane = (long long)p->Rp * (p->Cp / 2);
+            ch.wiener = p->wiener_half.p;
+            ch.wiener_tiled = p->wiener_half_tiled.p;
+            ch.K = p->K;
+            ch.tw = p->tw_cols;
+            {
+                KernelTimer kt(p, sh, 1, 4.0 * p->H * p->Cp + 8.0 * P);
+                if (p->col_split_half) {
+                    int nl = 0;
+                    FDR_CUDA(launch_col_split(ch, sh, &nl));
+                    p->launches += nl - 1;
+                } else {
+                    FDR_CUDA(launch_col_pass(ch, sh));
+                }
+                ColPassArgs cn = ch;  // the Nyquist column: one more column of the same problem
+                cn.pitch = 1;
+                cn.data = nyq;
+                cn.cplane = p->Rp;
+                cn.wiener = p->wiener_nyq.p;
+                cn.wiener_tiled = nullptr;
+                FDR_CUDA(launch_col_pass(cn, sh));
+            }
+            RowPassArgs h3{};
+            h3.n = p->Cp;
+            h3.nrows = p->Rp / 2;
+            h3.npairs = 1;
+            h3.pair_base = nu - 1;
+            h3.in_mode = ROW_IN_HALF;
+            h3.out_mode = ROW_OUT_REAL_ROWS2;
+            h3.unit_base = base;
+            h3.units_total = n_units;
+            h3.raw = raw_l;
+            h3.raw_unit_stride = HW;
+            h3.raw_rows = p->H;
+            h3.raw_cols = p->W;
+            h3.minmax = mm_l;
+            h3.local_units = nu;
+            h3.tw = p->tw_rows;
+            h3.pair_dist = p->Rp / 2;
+            h3.hp_peers[0] = hbuf;
+            h3.hp_shift = ilog2(p->Cp / 2);
+            h3.hp_plane = 0;
+            h3.nyq_peers[0] = nyq;
+            h3.nyq_world = 1;
+            h3.nyq_plane = 0;
+            {
+                KernelTimer kt(p, sh, 2, 4.0 * P + 4.0 * HW);
+                FDR_CUDA(launch_row_pass(h3, sh));
+            }
+            p->launches += 4;
+            if (sh != s) {
+                FDR_CUDA(cudaEventRecord(p->ev_half_join, sh));
+                FDR_CUDA(cudaStreamWaitEvent(s, p->ev_half_join, 0));
             }
         }
 
-        RowPassArgs r3{};
-        r3.n = p->Cp;
-        r3.nrows = p->Rp;
-        r3.npairs = np;
-        r3.in_mode = ROW_IN_COMPLEX;
-        r3.out_mode = ROW_OUT_REAL_PAIR;
-        r3.cin = spec_l;
-        r3.cplane = (long long)p->plane_elems();
-        r3.unit_base = base;
-        r3.units_total = n_units;
-        r3.raw = raw_l;
-        r3.raw_unit_stride = HW;
-        r3.raw_rows = p->H;
-        r3.raw_cols = p->W;
-        r3.minmax = mm_l;
-        r3.local_units = nu;
-        r3.tw = p->tw_rows;
-        {
-            KernelTimer kt(p, s, 2, 8.0 * P * np + 4.0 * HW * nu);
-            FDR_CUDA(launch_row_pass(r3, s));
-        }
-
         FDR_CUDA(launch_minmax_finalize(mm_l, ss_l, mmf_l, nu, s));
-        p->launches += 5;
+        p->launches += 2;
         if (out_u8 && p->white_balance && C == 3) {
             KernelTimer kt(p, s, 3, (2 * 12.0 + 3.0 + (in.mode == ROW_IN_PAIR_U8 ? 3.0 : 12.0)) * HW * (nu / 3));
             const uint8_t* o8 = in.mode == ROW_IN_PAIR_U8 ? in.u8 + base * HW : nullptr;
@@ -321,6 +456,9 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
             FDR_CUDA(cudaStreamWaitEvent(s_caller, p->lane_join[i], 0));
         }
     }
+    FDR_CUDA(cudaEventRecord(p->ev_last, s_caller));
+    p->last_stream = s_caller;
+    p->have_last = true;
     return FDR_OK;
 }
 
@@ -330,6 +468,7 @@ int build_wiener_into(fdr_plan* p, DevBuf<float2>& dst, bool split) {
     FDR_TRY(dst.ensure(p->plane_elems()));
     FDR_TRY(p->spec.ensure(p->plane_elems()));
     cudaStream_t s = p->stream;
+    if (p->have_last && p->last_stream != s) FDR_CUDA(cudaStreamWaitEvent(s, p->ev_last, 0));  // restores still using the workspace
     RowPassArgs r{};
     r.n = p->Cp;
     r.nrows = p->psf_rows;
@@ -384,6 +523,73 @@ struct ScopedTimer {  // event pair on a stream, accumulating into a bucket (Pro
     }
 };
 
+// Wiener factors of the half-plane path: columns 0 .. Cp/2-1 as a plane of pitch Cp/2 and the Nyquist column Cp/2, built
+// by the same kernels at that pitch (fft_serial.cpp:166-224 on those columns only).
+int build_wiener_half(fdr_plan* p) {
+    const int Ch = p->Cp / 2;
+    const size_t half_elems = (size_t)p->Rp * Ch;
+    cudaStream_t s = p->stream;
+    FDR_TRY(p->wiener_half.ensure(half_elems));
+    FDR_TRY(p->wiener_nyq.ensure((size_t)p->Rp));
+    DevBuf<float2> tmp;  // scratch of the in-place column passes: [Rp][Cp/2] + [Rp]
+    FDR_TRY(tmp.ensure(half_elems + p->Rp));
+    int rc = FDR_OK;
+    auto cu = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && rc == FDR_OK) rc = set_error(FDR_E_CUDA, "half-plane Wiener build (%s): %s", what, cudaGetErrorString(e));
+    };
+    RowPassArgs r{};  // the PSF's row spectrum again (the full build consumed it)
+    r.n = p->Cp;
+    r.nrows = p->psf_rows;
+    r.npairs = 1;
+    r.in_mode = ROW_IN_PAIR_F32;
+    r.out_mode = ROW_OUT_COMPLEX;
+    r.in_f32 = p->psf.p;
+    r.in_unit_stride = (long long)p->psf_rows * p->psf_cols;
+    r.in_row_stride = p->psf_cols;
+    r.channels = 1;
+    r.img_rows = p->psf_rows;
+    r.img_cols = p->psf_cols;
+    r.units_total = 1;
+    r.cout = p->spec.p;
+    r.cplane = (long long)p->plane_elems();
+    r.tw = p->tw_rows;
+    cu(launch_row_pass(r, s), "rows");
+    cu(cudaMemcpy2DAsync(tmp.p, (size_t)Ch * sizeof(float2), p->spec.p, (size_t)p->Cp * sizeof(float2), (size_t)Ch * sizeof(float2),
+                         p->psf_rows, cudaMemcpyDeviceToDevice, s), "left half");
+    cu(cudaMemcpy2DAsync(tmp.p + half_elems, sizeof(float2), p->spec.p + Ch, (size_t)p->Cp * sizeof(float2), sizeof(float2), p->psf_rows,
+                         cudaMemcpyDeviceToDevice, s), "nyquist column");
+    ColPassArgs c{};
+    c.n = p->Rp;
+    c.pitch = Ch;
+    c.npairs = 1;
+    c.mode = COL_MAKE_WIENER;
+    c.rows_valid = p->psf_rows;
+    c.data = tmp.p;
+    c.cplane = (long long)half_elems;
+    c.wiener_out = p->wiener_half.p;
+    c.K = p->K;
+    c.tw = p->tw_cols;
+    if (rc == FDR_OK) cu(p->col_split_half ? launch_col_split(c, s, nullptr) : launch_col_pass(c, s), "columns");
+    ColPassArgs n = c;
+    n.pitch = 1;
+    n.data = tmp.p + half_elems;
+    n.cplane = p->Rp;
+    n.wiener_out = p->wiener_nyq.p;
+    if (rc == FDR_OK) cu(launch_col_pass(n, s), "nyquist");
+    p->wiener_half_tiled.release();
+    ColPassArgs probe{};
+    probe.n = p->Rp;
+    probe.pitch = Ch;
+    probe.mode = COL_WIENER;
+    if (rc == FDR_OK && !p->col_split_half && col_wide_applicable(probe)) {
+        rc = p->wiener_half_tiled.ensure(half_elems);
+        if (rc == FDR_OK) cu(launch_wiener_retile(p->wiener_half.p, p->wiener_half_tiled.p, p->Rp, Ch, s), "retile");
+    }
+    cu(cudaStreamSynchronize(s), "sync");
+    tmp.release();
+    return rc;
+}
+
 int build_wiener(fdr_plan* p) {
     p->wiener_nat.release();
     FDR_TRY(build_wiener_into(p, p->wiener, p->col_split));
@@ -399,6 +605,7 @@ int build_wiener(fdr_plan* p) {
             FDR_CUDA(cudaStreamSynchronize(p->stream));
         }
     }
+    if (p->half_ok) FDR_TRY(build_wiener_half(p));
     p->have_wiener = true;
     return FDR_OK;
 }
@@ -487,14 +694,33 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
         }
         const char* ln = getenv("FDR_LANES");
         if (ln && atoi(ln) >= 1 && atoi(ln) <= 4) p->lanes = atoi(ln);
+        {
+            // half-plane path for the odd colour plane: from FDR_HALF_MIN_PIXELS padded pixels up (below that an image
+            // is launch-bound and the extra launches cost more than the saved traffic); FDR_HALF=0 disables it
+            const char* hv = getenv("FDR_HALF");
+            const char* hm = getenv("FDR_HALF_MIN_PIXELS");
+            const long long min_px = (hm && atoll(hm) >= 0) ? atoll(hm) : (1LL << 21);
+            p->half_ok = !(hv && atoi(hv) == 0) && p->Cp >= FDR_HALF_MIN_N && p->Rp >= 2 && (long long)p->Rp * p->Cp >= min_px;
+            ColPassArgs probe{};
+            probe.n = p->Rp;
+            probe.pitch = p->Cp / 2;
+            probe.mode = COL_WIENER;
+            const char* cs = getenv("FDR_COL_SPLIT");
+            p->col_split_half = p->half_ok && col_split_applicable(probe) && !(cs && atoi(cs) == 0);
+        }
     }
     cudaError_t e = get_twiddles(p->Cp, &p->tw_rows);
     if (e == cudaSuccess) e = get_twiddles(p->Rp, &p->tw_cols);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&p->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_last, cudaEventDisableTiming);
+    if (e == cudaSuccess && p->half_ok) e = cudaStreamCreateWithFlags(&p->s_half, cudaStreamNonBlocking);
+    if (e == cudaSuccess && p->half_ok) e = cudaEventCreateWithFlags(&p->ev_half_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess && p->half_ok) e = cudaEventCreateWithFlags(&p->ev_half_join, cudaEventDisableTiming);
     if (e != cudaSuccess) {
-        delete p;
-        return set_error(FDR_E_CUDA, "plan twiddle/stream/event creation: %s", cudaGetErrorString(e));
+        const int rc = set_error(FDR_E_CUDA, "plan twiddle/stream/event creation: %s", cudaGetErrorString(e));
+        fdr_plan_destroy(p);  // releases whatever was created
+        return rc;
     }
     *plan = p;
     return FDR_OK;
@@ -513,6 +739,9 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
     p->wiener.release();
     p->wiener_nat.release();
     p->wiener_tiled.release();
+    p->wiener_half.release();
+    p->wiener_half_tiled.release();
+    p->wiener_nyq.release();
     p->psf.release();
     p->d_in_u8.release();
     p->d_out_u8.release();
@@ -539,6 +768,10 @@ __attribute__((visibility("default"))) int fdr_plan_destroy(fdr_plan* p) {
         if (p->lane_join[i]) cudaEventDestroy(p->lane_join[i]);
     }
     if (p->lane_fork) cudaEventDestroy(p->lane_fork);
+    if (p->ev_last) cudaEventDestroy(p->ev_last);
+    if (p->ev_half_fork) cudaEventDestroy(p->ev_half_fork);
+    if (p->ev_half_join) cudaEventDestroy(p->ev_half_join);
+    if (p->s_half) cudaStreamDestroy(p->s_half);
     if (p->s_in) cudaStreamDestroy(p->s_in);
     if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -557,6 +790,12 @@ __attribute__((visibility("default"))) int fdr_plan_set_white_balance(fdr_plan* 
     if (!p) return set_error(FDR_E_INVALID, "plan is NULL");
     if (enabled && p->C != 3) return set_error(FDR_E_INVALID, "white balance needs 3-channel (BGR) images");
     p->white_balance = enabled != 0;
+    return FDR_OK;
+}
+
+__attribute__((visibility("default"))) int fdr_plan_half_plane(const fdr_plan* p, int* enabled) {
+    if (!p || !enabled) return set_error(FDR_E_INVALID, "bad arguments");
+    *enabled = p->half_ok ? 1 : 0;
     return FDR_OK;
 }
 
@@ -1003,13 +1242,14 @@ __attribute__((visibility("default"))) int fdr_dft_naive_host(float* data, int n
     FDR_CUDA(cudaGetDevice(&dev));
     FDR_TRY(ensure_device(dev));
     float2 *d = nullptr, *o = nullptr;
-    FDR_CUDA(cudaMalloc(&d, sizeof(float2) * n));
-    FDR_CUDA(cudaMalloc(&o, sizeof(float2) * n));
-    FDR_CUDA(cudaMemcpy(d, data, sizeof(float2) * n, cudaMemcpyHostToDevice));
-    FDR_CUDA(launch_dft_naive(d, o, n, 1, 1, n, inverse, 0));
-    FDR_CUDA(cudaMemcpy(data, o, sizeof(float2) * n, cudaMemcpyDeviceToHost));
-    cudaFree(d);
-    cudaFree(o);
+    cudaError_t e = cudaMalloc(&d, sizeof(float2) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&o, sizeof(float2) * n);
+    if (e == cudaSuccess) e = cudaMemcpy(d, data, sizeof(float2) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_dft_naive(d, o, n, 1, 1, n, inverse, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(data, o, sizeof(float2) * n, cudaMemcpyDeviceToHost);
+    if (d) cudaFree(d);
+    if (o) cudaFree(o);
+    if (e != cudaSuccess) return set_error(FDR_E_CUDA, "naive DFT: %s", cudaGetErrorString(e));
     return FDR_OK;
 }
 

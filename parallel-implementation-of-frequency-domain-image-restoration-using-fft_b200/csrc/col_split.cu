@@ -50,11 +50,9 @@ template <int LOGN1> static cudaError_t launch_strided(const ColSplitArgs& s, cu
     constexpr int N1 = 1 << LOGN1;
     constexpr int threads = N1 / 16 * SPLIT_CWC * SPLIT_NJ;
     constexpr size_t smem = (size_t)N1 * SPLIT_CWC * SPLIT_NJ * sizeof(float2);
-    static bool cfg = false;
-    if (!cfg && smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(col_split_strided_kernel<LOGN1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(col_split_strided_kernel<LOGN1>), smem);
         if (e != cudaSuccess) return e;
-        cfg = true;
     }
     dim3 grid(s.ncols / SPLIT_CWC, SPLIT_N2 / SPLIT_NJ, s.npairs);
     col_split_strided_kernel<LOGN1><<<grid, threads, smem, st>>>(s);

@@ -235,13 +235,9 @@ template <int LOGN, int CW = default_col_cw(LOGN)> static cudaError_t launch_t(c
     CUtensorMap tm_data, tm_w;
     if (!tma_make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
     if (!tma_make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
-    static unsigned long long configured = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured >> (dev & 63) & 1ULL)) {
-        cudaError_t e = cudaFuncSetAttribute(col_wiener_tma_kernel<LOGN, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(col_wiener_tma_kernel<LOGN, CW>), Gm::SMEM);
         if (e != cudaSuccess) return e;
-        configured |= 1ULL << (dev & 63);
     }
     dim3 grid(a.pitch / CW, a.npairs);
     col_wiener_tma_kernel<LOGN, CW><<<grid, Gm::THREADS, Gm::SMEM, s>>>(tm_data, tm_w, a);
@@ -255,19 +251,13 @@ template <int LOGN, int CW = default_col_cw(LOGN)> static cudaError_t launch_pip
     CUtensorMap tm_data, tm_w;
     if (!tma_make_map(&tm_data, a.data, (long long)(a.pair_base + a.npairs) * a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
     if (!tma_make_map(&tm_w, a.wiener, a.n, a.pitch, CW, BOX_ROWS)) return cudaErrorInvalidValue;
-    static unsigned long long configured = 0;
-    static int sms[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured >> (dev & 63) & 1ULL)) {
-        cudaError_t e = cudaFuncSetAttribute(col_wiener_pipe_kernel<LOGN, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pg::SMEM);
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(col_wiener_pipe_kernel<LOGN, CW>), Pg::SMEM);
         if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        configured |= 1ULL << (dev & 63);
     }
+    const int nsm = device_sm_count();
     const int tiles_x = a.pitch / CW, ntiles = tiles_x * a.npairs;
-    const int grid = ntiles < sms[dev & 63] ? ntiles : sms[dev & 63];
+    const int grid = ntiles < nsm ? ntiles : nsm;
     col_wiener_pipe_kernel<LOGN, CW><<<grid, Pg::THREADS, Pg::SMEM, s>>>(tm_data, tm_w, a, tiles_x, ntiles);
     return cudaGetLastError();
 }

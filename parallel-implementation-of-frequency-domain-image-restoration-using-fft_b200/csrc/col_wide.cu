@@ -298,14 +298,8 @@ template <int LOGN, int CW, int PROBE = 0> static cudaError_t launch_wide_t(cons
     const float2* tw = nullptr;
     cudaError_t e = wide_twiddles<Gm::N>(&tw);
     if (e != cudaSuccess) return e;
-    static unsigned long long configured = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured >> (dev & 63) & 1ULL)) {
-        e = cudaFuncSetAttribute(col_wiener_wide_kernel<LOGN, CW, PROBE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
-        if (e != cudaSuccess) return e;
-        configured |= 1ULL << (dev & 63);
-    }
+    e = ensure_dyn_smem(reinterpret_cast<const void*>(col_wiener_wide_kernel<LOGN, CW, PROBE>), Gm::SMEM);
+    if (e != cudaSuccess) return e;
     const int grid = (a.pitch / CW) * a.npairs;
     col_wiener_wide_kernel<LOGN, CW, PROBE><<<grid, Gm::THREADS, Gm::SMEM, s>>>(tm_data, tm_w, a, tw);
     return cudaGetLastError();
@@ -338,11 +332,9 @@ template <int BW> static cudaError_t launch_copy_probe(const ColPassArgs& a, cud
     CUtensorMap tm;
     const long long rows = (long long)(a.pair_base + a.npairs) * a.n;
     if (!tma_make_map(&tm, a.data, rows, a.pitch, BW, 256)) return cudaErrorInvalidValue;
-    static bool cfg = false;
-    if (!cfg) {
-        cudaError_t e = cudaFuncSetAttribute(tma_copy_probe_kernel<BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 69632);
+    {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(tma_copy_probe_kernel<BW>), 69632);
         if (e != cudaSuccess) return e;
-        cfg = true;
     }
     const int tiles_x = a.pitch / BW;
     const long long grid = (long long)tiles_x * (rows / (8192 / BW));
@@ -385,19 +377,11 @@ template <int LOGN, int CW> static cudaError_t launch_wide_pipe_t(const ColPassA
     const float2* tw = nullptr;
     cudaError_t e = wide_twiddles<Gm::N>(&tw);
     if (e != cudaSuccess) return e;
-    static unsigned long long configured = 0;
-    static int sms[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(configured >> (dev & 63) & 1ULL)) {
-        e = cudaFuncSetAttribute(col_wiener_wide_pipe_kernel<LOGN, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pg::SMEM);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        configured |= 1ULL << (dev & 63);
-    }
+    e = ensure_dyn_smem(reinterpret_cast<const void*>(col_wiener_wide_pipe_kernel<LOGN, CW>), Pg::SMEM);
+    if (e != cudaSuccess) return e;
+    const int nsm = device_sm_count();
     const int tiles_x = a.pitch / CW, ntiles = tiles_x * a.npairs;
-    const int grid = ntiles < sms[dev & 63] ? ntiles : sms[dev & 63];
+    const int grid = ntiles < nsm ? ntiles : nsm;
     col_wiener_wide_pipe_kernel<LOGN, CW><<<grid, Pg::THREADS, Pg::SMEM, s>>>(tm_data, tm_w, a, tw, tiles_x, ntiles);
     return cudaGetLastError();
 }

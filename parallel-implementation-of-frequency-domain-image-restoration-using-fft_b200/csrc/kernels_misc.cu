@@ -97,29 +97,50 @@ __global__ void minmax_finalize_kernel(const unsigned int* mm, float2* ss, float
         mmf[2 * i + 1] = (float)smax;
     }
 }
-__global__ void minmax_decode_kernel(const unsigned int* mm, float* mmf, int units) {
+// negate_max: the vector holds (min, -max), so that a single all-reduce(MIN) across ranks folds both extrema
+__global__ void minmax_decode_kernel(const unsigned int* mm, float* mmf, int units, int negate_max) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= units) return;
     unsigned int lo, hi;
     minmax_fold(mm, i, lo, hi);
+    const float mx = f32_from_ordered(hi);
     mmf[2 * i] = f32_from_ordered(lo);
-    mmf[2 * i + 1] = f32_from_ordered(hi);
+    mmf[2 * i + 1] = negate_max ? -mx : mx;
 }
-cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, cudaStream_t s) {
-    minmax_decode_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax, minmax_f32, units);
+cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, int negate_max, cudaStream_t s) {
+    minmax_decode_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax, minmax_f32, units, negate_max);
     return cudaGetLastError();
 }
 
-__global__ void scale_shift_from_f32_kernel(const float* mmf, float2* ss, int units) {
+__global__ void scale_shift_from_f32_kernel(const float* mmf, float2* ss, int units, int negated_max) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= units) return;
-    const double smin = (double)mmf[2 * i], smax = (double)mmf[2 * i + 1];
+    const double smin = (double)mmf[2 * i], smax = negated_max ? -(double)mmf[2 * i + 1] : (double)mmf[2 * i + 1];
     const double scale = (smax - smin) > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0;
     const float a = (float)scale;
     ss[i] = make_float2(a, 0.0f - (float)__dmul_rn(smin, (double)a));
 }
-cudaError_t launch_scale_shift_from_f32(const float* minmax_f32, float2* scale_shift, int units, cudaStream_t s) {
-    scale_shift_from_f32_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax_f32, scale_shift, units);
+cudaError_t launch_scale_shift_from_f32(const float* minmax_f32, float2* scale_shift, int units, int negated_max, cudaStream_t s) {
+    scale_shift_from_f32_kernel<<<(units + 127) / 128, 128, 0, s>>>(minmax_f32, scale_shift, units, negated_max);
+    return cudaGetLastError();
+}
+
+// Column N/2 of the PSF's row spectra without a transform: H_y[N/2] = sum_x h[y][x] * (-1)^x (real).  One thread per PSF
+// row; rows are a few hundred pixels at most.
+__global__ void psf_nyquist_kernel(const float* __restrict__ psf, int rows, int cols, float2* __restrict__ out) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= rows) return;
+    const float* r = psf + (size_t)y * cols;
+    float even = 0.f, odd = 0.f;
+    for (int x = 0; x + 1 < cols; x += 2) {
+        even += r[x];
+        odd += r[x + 1];
+    }
+    if (cols & 1) even += r[cols - 1];
+    out[y] = make_float2(even - odd, 0.f);
+}
+cudaError_t launch_psf_nyquist(const float* psf, int rows, int cols, float2* out, cudaStream_t s) {
+    psf_nyquist_kernel<<<(rows + 63) / 64, 64, 0, s>>>(psf, rows, cols, out);
     return cudaGetLastError();
 }
 

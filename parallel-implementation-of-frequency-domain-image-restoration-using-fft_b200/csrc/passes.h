@@ -23,8 +23,20 @@ constexpr int FDR_MINMAX_SLOTS = 128;  // atomic slots per plane for the min/max
 // GPU, its columns are spread over `world` column slabs [rows_padded][n/world], one per GPU, reached
 // through peer-mapped pointers (NVLink).  The transpose of the reference's MPI_Alltoallv
 // (/root/reference/fft/fft_mpi.cpp:170-279) is thereby fused into the row passes.
-enum RowInMode { ROW_IN_PAIR_F32 = 0, ROW_IN_PAIR_U8 = 1, ROW_IN_COMPLEX = 2, ROW_IN_GATHER = 3 };
-enum RowOutMode { ROW_OUT_COMPLEX = 0, ROW_OUT_REAL_PAIR = 1, ROW_OUT_SCATTER = 2 };
+//
+// HALF-PLANE forms (one real plane per transform instead of a pair of planes): rows y and y + D of the SAME plane are
+// packed as z = row_y + i*row_{y+D}; the row spectra of real rows are Hermitian, so after untangling
+//   X_y[k] = (Z[k] + conj Z[N-k]) / 2,   X_{y+D}[k] = (Z[k] - conj Z[N-k]) / (2i)
+// only columns 0 .. N/2-1 are stored (a half-width plane [rows][N/2]) plus the real Nyquist column k = N/2 in a side
+// vector.  The column pass then runs on half the columns, and the inverse row pass rebuilds Z[k] and Z[N-k] from the
+// half plane (ROW_IN_HALF).  An odd colour plane (the R of BGR) therefore costs half of a pair instead of a whole pair:
+// -25 % of passes 1-3 for one RGB image and -25 % of the NVLink volume of the row-sharded path.  The reference has no
+// counterpart (it transforms every channel as a full complex plane, /root/reference/fft/fft_gpu.cu:325-368).
+enum RowInMode { ROW_IN_PAIR_F32 = 0, ROW_IN_PAIR_U8 = 1, ROW_IN_COMPLEX = 2, ROW_IN_GATHER = 3,
+                 ROW_IN_ROWS2_F32 = 4, ROW_IN_ROWS2_U8 = 5, ROW_IN_HALF = 6 };
+enum RowOutMode { ROW_OUT_COMPLEX = 0, ROW_OUT_REAL_PAIR = 1, ROW_OUT_SCATTER = 2, ROW_OUT_HALF = 3, ROW_OUT_REAL_ROWS2 = 4 };
+constexpr int FDR_MAX_PEERS = 16;
+constexpr int FDR_HALF_MIN_N = 64;  // shortest row length the half-plane forms are instantiated for
 enum ColMode { COL_FFT = 0, COL_WIENER = 1, COL_MAKE_WIENER = 2, COL_FILTER = 3, COL_COPY = 4 /* timing probe: load + store only */ };
 
 struct RowPassArgs {
@@ -62,6 +74,17 @@ struct RowPassArgs {
     long long peer_plane;        // elements per pair in a slab = rows_padded * (n / world)
     int row0;                    // global (padded) index of local row 0
     int max_ctas;                // > 0: scatter / gather passes run as at most this many persistent CTAs per pair
+    // ---- half-plane forms (ROW_IN_ROWS2_*, ROW_OUT_HALF, ROW_IN_HALF, ROW_OUT_REAL_ROWS2): blockIdx.y counts PLANES ----
+    int pair_dist;               // D: row `r` of the launch carries rows r and r + D (local indices, like `row0 + r` globally)
+    int rows_in;                 // ROWS2 input: local rows present; the second row reads as zero when r + D >= rows_in
+    int hp_rows_store;           // ROW_OUT_HALF: global rows >= this are not stored (the image height; the column pass zero-fills)
+    float2* hp_peers[FDR_MAX_PEERS];  // half planes by column owner: column k < n/2 of plane u, global row g at
+                                      // hp_peers[k >> hp_shift] + u*hp_plane + (g << hp_shift) + (k & mask); one entry when unsharded
+    int hp_shift;                // log2(columns of the half plane per owner)
+    long long hp_plane;          // elements per plane in a half-plane slab = rows_padded << hp_shift
+    float2* nyq_peers[FDR_MAX_PEERS]; // Nyquist columns: plane u, global row g at nyq_peers[u % nyq_world] + u*nyq_plane + g
+    int nyq_world;
+    long long nyq_plane;         // = rows_padded
 };
 
 struct ColPassArgs {
@@ -88,6 +111,11 @@ struct ColPassArgs {
                           // 7 = wide core, persistent + pipelined
 };
 
+// Opt-in to more than 48 KB of dynamic shared memory for `func` on the CURRENT device; done once per (function, device),
+// thread-safe (several plans or shards on different devices may launch from different host threads).
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
+// SM count of the current device (cached per device).
+int device_sm_count();
 // Launchers (defined in passes_*.cu).  Return cudaGetLastError() of the launch.
 cudaError_t launch_row_pass(const RowPassArgs& a, cudaStream_t s);
 cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s);
@@ -138,8 +166,11 @@ cudaError_t launch_normalize_f32(const float* raw, long long raw_unit_stride, co
                                  long long out_unit_stride, int units, int rows, int cols, cudaStream_t s);
 cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, long long plane_px,
                             long long px0, long long npx, cudaStream_t s);
-cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, cudaStream_t s);
-cudaError_t launch_scale_shift_from_f32(const float* minmax_f32, float2* scale_shift, int units, cudaStream_t s);
+// negate_max / negated_max: the f32 vector holds (min, -max) per plane (one all-reduce(MIN) across ranks folds both)
+cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, int negate_max, cudaStream_t s);
+cudaError_t launch_scale_shift_from_f32(const float* minmax_f32, float2* scale_shift, int units, int negated_max, cudaStream_t s);
+// out[y] = column n/2 of the row spectrum of PSF row y (real): sum_x psf[y][x] * (-1)^x
+cudaError_t launch_psf_nyquist(const float* psf, int rows, int cols, float2* out, cudaStream_t s);
 // out-of-place batched O(n^2) DFT: element i of batch b at in[b*batch_stride + i*elem_stride]
 cudaError_t launch_dft_naive(const float2* in, float2* out, int n, long long elem_stride, int batch,
                              long long batch_stride, int inverse, cudaStream_t s);

@@ -15,6 +15,36 @@ namespace fdr {
 FDR_ALL_LOGNS
 #undef X
 
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find({func, dev});
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    done[{func, dev}] = bytes;
+    return cudaSuccess;
+}
+
+int device_sm_count() {
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    cache[dev] = n;
+    return n;
+}
+
 static int ilog2_exact(int n) {
     if (n <= 0 || (n & (n - 1))) return -1;
     int l = 0;

@@ -36,23 +36,27 @@ template <int LOGN> struct RowGeom {
     static constexpr size_t SMEM = fft_smem_bytes<N, 1>() * RPC * (DB ? 2 : 1);
 };
 
-// One block of RPC rows of pair blockIdx.y; `row_block` is blockIdx.x in the one-shot kernel and the loop
-// index in the persistent one.
+// One block of RPC rows of pair (half-plane forms: plane) blockIdx.y; `row_block` is blockIdx.x in the one-shot kernel
+// and the loop index in the persistent one.
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
 __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int row_block) {
     using Gm = RowGeom<LOGN>;
     constexpr int N = Gm::N, E = Gm::E, T = Gm::T, RPC = Gm::RPC;
+    constexpr bool IN_ROWS2 = (IN_MODE == ROW_IN_ROWS2_F32 || IN_MODE == ROW_IN_ROWS2_U8);
+    constexpr bool HALF = IN_ROWS2 || IN_MODE == ROW_IN_HALF || OUT_MODE == ROW_OUT_HALF || OUT_MODE == ROW_OUT_REAL_ROWS2;
+    static_assert(!HALF || (E == 16 && N >= FDR_HALF_MIN_N), "half-plane forms need 16 points per thread");
+    constexpr int H8 = E / 2;  // points of the lower half spectrum per thread
     extern __shared__ float2 smem2[];
     const int tid = threadIdx.x;
     const int rl = (RPC > 1) ? (tid / T) : 0;
     const int t = (RPC > 1) ? (tid % T) : tid;
     const int row = row_block * RPC + rl;
-    const int pair = blockIdx.y + a.pair_base;
+    const int pair = blockIdx.y + a.pair_base;  // half-plane forms: the plane (local unit)
     const bool active = row < a.nrows;
     float2* ex = smem2 + (size_t)rl * Gm::EXW * (Gm::DB ? 2 : 1);
 
-    const long long u0 = 2LL * pair, u1 = u0 + 1;  // local units
-    const bool has1 = (a.unit_base + u1) < a.units_total;
+    const long long u0 = HALF ? (long long)pair : 2LL * pair, u1 = HALF ? u0 : u0 + 1;  // local units
+    const bool has1 = HALF ? true : (a.unit_base + u1) < a.units_total;
 
     float2 v[E];
     if constexpr (IN_MODE == ROW_IN_COMPLEX) {
@@ -77,10 +81,55 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
             }
             v[m] = z;
         }
-    } else if constexpr (IN_MODE == ROW_IN_PAIR_F32) {
+    } else if constexpr (IN_MODE == ROW_IN_HALF) {
+        // The half plane holds conj(Y_y[k]) for k < N/2 (what the column pass leaves behind).  With A = stored row y, B = stored
+        // row y + D, the packed inverse input conj(Z), Z = Y_y + i Y_{y+D} (Hermitian extension), is
+        //   conj Z[k]   = A - i B            = (A.x + B.y,  A.y - B.x)
+        //   conj Z[N-k] = conj(A) - i conj(B) = (A.x - B.y, -A.y - B.x)
+        // the mirrored value belongs to thread T - t, register E-1-m: one shared-memory exchange.
+        const int mask = (1 << a.hp_shift) - 1;
+        const long long b1 = (long long)pair * a.hp_plane + ((long long)(a.row0 + row) << a.hp_shift);
+        const long long b2 = b1 + ((long long)a.pair_dist << a.hp_shift);
+        float2 mv[H8];
+#pragma unroll
+        for (int m = 0; m < H8; ++m) {
+            const int k = t + T * m;
+            float2 A = make_float2(0.f, 0.f), B = A;
+            if (active) {
+                const float2* src = a.hp_peers[k >> a.hp_shift];
+                A = src[b1 + (k & mask)];
+                B = src[b2 + (k & mask)];
+            }
+            v[m] = make_float2(A.x + B.y, A.y - B.x);
+            mv[m] = make_float2(A.x - B.y, -(A.y + B.x));
+        }
+#pragma unroll
+        for (int m = 0; m < H8; ++m) ex[(H8 - m) * T - t] = mv[m];  // (t = 0, m = 0 lands in the spare word H8*T)
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < H8; ++j) v[H8 + j] = ex[j * T + t];
+        if (t == 0) {  // Nyquist column: word 0 was written by nobody
+            float2 A = make_float2(0.f, 0.f), B = A;
+            if (active) {
+                const float2* nq = a.nyq_peers[pair % a.nyq_world] + (long long)pair * a.nyq_plane + a.row0 + row;
+                A = nq[0];
+                B = nq[a.pair_dist];
+            }
+            v[H8] = make_float2(A.x + B.y, A.y - B.x);
+        }
+        // (the first exchange of the transform starts with a barrier: these reads are done before `ex` is reused)
+    } else if constexpr (IN_MODE == ROW_IN_PAIR_F32 || IN_MODE == ROW_IN_ROWS2_F32) {
         const float* p0 = a.in_f32 + (a.unit_base + u0) * a.in_unit_stride + (long long)row * a.in_row_stride;
-        const float* p1 = has1 ? a.in_f32 + (a.unit_base + u1) * a.in_unit_stride + (long long)row * a.in_row_stride : p0;
-        const float k1 = has1 ? 1.f : 0.f;
+        const float* p1;
+        float k1;
+        if constexpr (IN_ROWS2) {
+            const bool has2 = row + a.pair_dist < a.rows_in;
+            p1 = has2 ? p0 + (long long)a.pair_dist * a.in_row_stride : p0;
+            k1 = has2 ? 1.f : 0.f;
+        } else {
+            p1 = has1 ? a.in_f32 + (a.unit_base + u1) * a.in_unit_stride + (long long)row * a.in_row_stride : p0;
+            k1 = has1 ? 1.f : 0.f;
+        }
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int x = t + T * m;
@@ -91,16 +140,28 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
             }
             v[m] = z;
         }
-    } else {  // ROW_IN_PAIR_U8 : x * (float)(1/255.)  (serial.cpp:24-25 convertTo + /= 255.0)
-        const long long g0 = a.unit_base + u0, g1 = has1 ? a.unit_base + u1 : g0;
+    } else {  // ROW_IN_PAIR_U8 / ROW_IN_ROWS2_U8 : x * (float)(1/255.)  (serial.cpp:24-25 convertTo + /= 255.0)
         const float inv255 = (float)(1.0 / 255.0);
-        const float k1 = has1 ? inv255 : 0.f;
+        const long long g0 = a.unit_base + u0;
+        long long g1;
+        int row1;       // second operand: plane g1, row row1
+        float k1;
+        if constexpr (IN_ROWS2) {
+            const bool has2 = row + a.pair_dist < a.rows_in;
+            g1 = g0;
+            row1 = has2 ? row + a.pair_dist : row;
+            k1 = has2 ? inv255 : 0.f;
+        } else {
+            g1 = has1 ? a.unit_base + u1 : g0;
+            row1 = row;
+            k1 = has1 ? inv255 : 0.f;
+        }
         if (a.channels == 3) {
             // BGR fast path: compile-time pixel stride, so every load is base + immediate
             const long long i0 = g0 / 3, i1 = g1 / 3;
             const int c0 = (int)(g0 - i0 * 3), c1 = (int)(g1 - i1 * 3);
             const uint8_t* p0 = a.in_u8 + ((i0 * a.img_rows + row) * (long long)a.img_cols) * 3 + c0 + 3 * t;
-            const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row) * (long long)a.img_cols) * 3 + c1 + 3 * t;
+            const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row1) * (long long)a.img_cols) * 3 + c1 + 3 * t;
             if (active && a.img_cols == N) {
                 const float nb0 = -8388608.0f * inv255, nb1 = -8388608.0f * k1;
 #pragma unroll
@@ -122,7 +183,7 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
             const long long i0 = g0 / C, i1 = g1 / C;
             const int c0 = (int)(g0 - i0 * C), c1 = (int)(g1 - i1 * C);
             const uint8_t* p0 = a.in_u8 + ((i0 * a.img_rows + row) * (long long)a.img_cols) * C + c0;
-            const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row) * (long long)a.img_cols) * C + c1;
+            const uint8_t* p1 = a.in_u8 + ((i1 * a.img_rows + row1) * (long long)a.img_cols) * C + c1;
 #pragma unroll
             for (int m = 0; m < E; ++m) {
                 const int x = t + T * m;
@@ -138,7 +199,39 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
 
     fft_forward<N, 1, Gm::DB>(v, ex, a.tw, t, 0);
 
-    if constexpr (OUT_MODE == ROW_OUT_SCATTER) {
+    if constexpr (OUT_MODE == ROW_OUT_HALF) {
+        // Untangle Z = FFT(row_y + i row_{y+D}): thread t needs Z[N - k] for its k = t + T*m (m < 8), held by thread T - t
+        // in register E-1-m.  Every thread parks its upper half in shared memory as word (j, t) = j*T + t (j = m - 8), thread
+        // 0 adds Z[0] as word 8*T, and the mirror of (t, m) is read from word (8 - m)*T - t -- also right for t = 0.
+        __syncthreads();  // the last exchange of the transform may still be read
+#pragma unroll
+        for (int j = 0; j < H8; ++j) ex[j * T + t] = v[H8 + j];
+        if (t == 0) ex[H8 * T] = v[0];
+        __syncthreads();
+        const int gy = a.row0 + row, gy2 = gy + a.pair_dist;
+        const bool st1 = active && gy < a.hp_rows_store, st2 = active && gy2 < a.hp_rows_store;
+        const int mask = (1 << a.hp_shift) - 1;
+        const long long b1 = (long long)pair * a.hp_plane + ((long long)gy << a.hp_shift);
+        const long long b2 = (long long)pair * a.hp_plane + ((long long)gy2 << a.hp_shift);
+#pragma unroll
+        for (int m = 0; m < H8; ++m) {
+            const float2 z = v[m], zm = ex[(H8 - m) * T - t];
+            const int k = t + T * m;
+            float2* dst = a.hp_peers[k >> a.hp_shift];
+            if (dst) {
+                if (st1) dst[b1 + (k & mask)] = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+                if (st2) dst[b2 + (k & mask)] = make_float2(0.5f * (z.y + zm.y), 0.5f * (zm.x - z.x));
+            }
+        }
+        if (t == 0) {  // Z[N/2] = X_y[N/2] + i X_{y+D}[N/2], both real
+            float2* nq = a.nyq_peers[pair % a.nyq_world];
+            if (nq) {
+                nq += (long long)pair * a.nyq_plane;
+                if (st1) nq[gy] = make_float2(v[H8].x, 0.f);
+                if (st2) nq[gy2] = make_float2(v[H8].y, 0.f);
+            }
+        }
+    } else if constexpr (OUT_MODE == ROW_OUT_SCATTER) {
         if (active) {
             const int cl_mask = (1 << a.peer_shift) - 1;
             const long long off = (long long)pair * a.peer_plane + ((long long)(a.row0 + row) << a.peer_shift);
@@ -161,7 +254,8 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
         }
     } else {
         // inverse row pass of the restoration: input was conj(column result), so the restored
-        // pair is conj(v): plane a = v.x, plane b = -v.y.
+        // pair is conj(v): plane a = v.x, plane b = -v.y.  (ROW_OUT_REAL_ROWS2: row y = v.x, row y + D = -v.y of ONE plane.)
+        constexpr bool ROWS2 = (OUT_MODE == ROW_OUT_REAL_ROWS2);
         float mn0 = INFINITY, mx0 = -INFINITY, mn1 = INFINITY, mx1 = -INFINITY;
         if (active) {
 #pragma unroll
@@ -172,32 +266,38 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
                 mn1 = fminf(mn1, v[m].y);
                 mx1 = fmaxf(mx1, v[m].y);
             }
-            if (row < a.raw_rows) {
-                float* d0 = a.raw + u0 * a.raw_unit_stride + (long long)row * a.raw_cols + t;
-                float* d1 = a.raw + u1 * a.raw_unit_stride + (long long)row * a.raw_cols + t;
-                if (a.raw_cols == N && has1) {  // un-cropped width, full pair: no per-element predicates
+            const int r0 = row, r1 = ROWS2 ? row + a.pair_dist : row;
+            const bool w0 = r0 < a.raw_rows, w1 = has1 && r1 < a.raw_rows;
+            float* d0 = a.raw + u0 * a.raw_unit_stride + (long long)r0 * a.raw_cols + t;
+            float* d1 = a.raw + u1 * a.raw_unit_stride + (long long)r1 * a.raw_cols + t;
+            if (a.raw_cols == N && w0 && w1) {  // un-cropped width, both rows stored: no per-element predicates
 #pragma unroll
-                    for (int m = 0; m < E; ++m) {
-                        d0[T * m] = v[m].x;
-                        d1[T * m] = v[m].y;
-                    }
-                } else {
+                for (int m = 0; m < E; ++m) {
+                    d0[T * m] = v[m].x;
+                    d1[T * m] = v[m].y;
+                }
+            } else if (w0 || w1) {
 #pragma unroll
-                    for (int m = 0; m < E; ++m) {
-                        if (t + T * m < a.raw_cols) {
-                            d0[T * m] = v[m].x;
-                            if (has1) d1[T * m] = v[m].y;
-                        }
+                for (int m = 0; m < E; ++m) {
+                    if (t + T * m < a.raw_cols) {
+                        if (w0) d0[T * m] = v[m].x;
+                        if (w1) d1[T * m] = v[m].y;
                     }
                 }
             }
+        }
+        if constexpr (ROWS2) {  // both halves belong to the same plane
+            mn0 = fminf(mn0, mn1);
+            mx0 = fmaxf(mx0, mx1);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
             mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
-            mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+            if constexpr (!ROWS2) {
+                mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+                mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+            }
         }
         __shared__ float red[32][4];
         const int warp = tid >> 5, lane = tid & 31;
@@ -226,7 +326,7 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
                 unsigned int* m0 = a.minmax + (u0 * FDR_MINMAX_SLOTS + slot) * 2;
                 atomicMin(m0, f32_ordered(mn0));
                 atomicMax(m0 + 1, f32_ordered(mx0));
-                if (has1) {
+                if (has1 && !ROWS2) {
                     unsigned int* m1 = a.minmax + (u1 * FDR_MINMAX_SLOTS + slot) * 2;
                     atomicMin(m1, f32_ordered(mn1));
                     atomicMax(m1 + 1, f32_ordered(mx1));
@@ -340,29 +440,15 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row_variant(const RowPassArgs& a, cudaStream_t s) {
     using Gm = RowGeom<LOGN>;
     if (Gm::SMEM > 48 * 1024) {
-        static unsigned long long configured = 0;  // bit per device ordinal
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!(configured >> (dev & 63) & 1ULL)) {
-            cudaError_t e = cudaFuncSetAttribute(row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
-            if (e != cudaSuccess) return e;
-            configured |= 1ULL << (dev & 63);
-        }
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ>), Gm::SMEM);
+        if (e != cudaSuccess) return e;
     }
     dim3 grid((a.nrows + Gm::RPC - 1) / Gm::RPC, a.npairs);
-    if constexpr (IN_MODE == ROW_IN_GATHER || OUT_MODE == ROW_OUT_SCATTER) {
+    if constexpr (IN_MODE == ROW_IN_GATHER || OUT_MODE == ROW_OUT_SCATTER || ((IN_MODE == ROW_IN_HALF || OUT_MODE == ROW_OUT_HALF) && LOGN >= 10)) {
         if (a.max_ctas > 0 && (unsigned)a.max_ctas < grid.x) {
             if (Gm::SMEM > 48 * 1024) {
-                static unsigned long long configured_p = 0;
-                int dev = 0;
-                cudaGetDevice(&dev);
-                if (!(configured_p >> (dev & 63) & 1ULL)) {
-                    cudaError_t e = cudaFuncSetAttribute(row_pass_persist_kernel<LOGN, IN_MODE, OUT_MODE, CONJ>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
-                    if (e != cudaSuccess) return e;
-                    configured_p |= 1ULL << (dev & 63);
-                }
+                cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(row_pass_persist_kernel<LOGN, IN_MODE, OUT_MODE, CONJ>), Gm::SMEM);
+                if (e != cudaSuccess) return e;
             }
             grid.x = a.max_ctas;
             row_pass_persist_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
@@ -380,6 +466,11 @@ template <int LOGN> cudaError_t launch_row_pass_t(const RowPassArgs& a, cudaStre
     if (a.in_mode == ROW_IN_PAIR_U8 && a.out_mode == ROW_OUT_SCATTER) return launch_row_variant<LOGN, ROW_IN_PAIR_U8, ROW_OUT_SCATTER, false>(a, s);
     if (a.in_mode == ROW_IN_PAIR_F32 && a.out_mode == ROW_OUT_SCATTER) return launch_row_variant<LOGN, ROW_IN_PAIR_F32, ROW_OUT_SCATTER, false>(a, s);
     if (a.in_mode == ROW_IN_GATHER && a.out_mode == ROW_OUT_REAL_PAIR) return launch_row_variant<LOGN, ROW_IN_GATHER, ROW_OUT_REAL_PAIR, false>(a, s);
+    if constexpr ((1 << LOGN) >= FDR_HALF_MIN_N) {  // half-plane forms (one real plane per transform)
+        if (a.in_mode == ROW_IN_ROWS2_U8 && a.out_mode == ROW_OUT_HALF) return launch_row_variant<LOGN, ROW_IN_ROWS2_U8, ROW_OUT_HALF, false>(a, s);
+        if (a.in_mode == ROW_IN_ROWS2_F32 && a.out_mode == ROW_OUT_HALF) return launch_row_variant<LOGN, ROW_IN_ROWS2_F32, ROW_OUT_HALF, false>(a, s);
+        if (a.in_mode == ROW_IN_HALF && a.out_mode == ROW_OUT_REAL_ROWS2) return launch_row_variant<LOGN, ROW_IN_HALF, ROW_OUT_REAL_ROWS2, false>(a, s);
+    }
     if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_COMPLEX && !a.conj)
         return launch_row_variant<LOGN, ROW_IN_COMPLEX, ROW_OUT_COMPLEX, false>(a, s);
     if (a.in_mode == ROW_IN_COMPLEX && a.out_mode == ROW_OUT_COMPLEX && a.conj)
@@ -390,15 +481,8 @@ template <int LOGN> cudaError_t launch_row_pass_t(const RowPassArgs& a, cudaStre
 template <int LOGN, int CW, int MODE, bool CONJ> cudaError_t launch_col_variant(const ColPassArgs& a, cudaStream_t s) {
     using Gm = ColGeom<LOGN, CW>;
     if (Gm::SMEM > 48 * 1024) {
-        static unsigned long long configured = 0;  // bit per device ordinal
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (!(configured >> (dev & 63) & 1ULL)) {
-            cudaError_t e = cudaFuncSetAttribute(col_pass_kernel<LOGN, CW, MODE, CONJ>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
-            if (e != cudaSuccess) return e;
-            configured |= 1ULL << (dev & 63);
-        }
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(col_pass_kernel<LOGN, CW, MODE, CONJ>), Gm::SMEM);
+        if (e != cudaSuccess) return e;
     }
     dim3 grid((a.pitch + CW - 1) / CW, a.npairs);
     col_pass_kernel<LOGN, CW, MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);

@@ -20,6 +20,13 @@
 //   2 exchanges per plane pair instead of the reference's 6 MPI_Alltoallv per channel
 //   (fft_mpi.cpp:386,393,423).  No scatter/gather to a root: every rank reads and writes only
 //   its own rows of the image.
+// HALF-PLANE MODE (default when the geometry allows it; FDR_SHARD_HALF=0 selects the plane-pair form above): every colour
+// plane is its own pipeline unit.  Phase 1 packs local rows y and y + D of ONE plane into a complex row transform, untangles
+// the two Hermitian row spectra and scatters only columns 0 .. Cp/2-1 (slab [C][Rp][Cl/2] per rank) plus the real Nyquist
+// column (a vector [Rp] on rank `plane % world`); phase 2 runs on half the columns; phase 3 rebuilds the packed rows from
+// the half planes.  For BGR that is 3 x 1/2 = 1.5 complex planes through NVLink and through the column phase instead of 2
+// (-25 %), and three equal units that the driver (fdr_dist.ShardedRestorer) runs as a pipeline: unit u's NVLink-bound row
+// phases overlap unit u-1's HBM-bound column phase.  The API keeps its names: a "pair" index is the unit index.
 // Several shards may live in one process on one device (peers = plain device pointers): that is
 // how the single-GPU test suite exercises this code.
 #include <cstring>
@@ -53,26 +60,85 @@ struct fdr_shard {
     const float2* tw_cols = nullptr;
     long long launches = 0;
     bool col_split = false;
+    // half-plane mode
+    bool half = false;
+    int units = 0;              // pipeline units: plane pairs, or planes in half-plane mode
+    int Ch = 0;                 // columns of a half plane per rank = Cl / 2
+    size_t nyq_off = 0;         // element offset of the Nyquist vectors [C][Rp] inside the slab allocation
+    DevBuf<float2> wiener_nyq;  // [Rp]
+    std::vector<float2*> peer_host;  // host copy of the peer slab table
+    int row_ctas = 0;           // > 0: exchange passes run as at most this many persistent CTAs per unit
+    int minmax_neg = 0;         // mmf holds (min, -max): one all-reduce(MIN) folds both
 };
 
 namespace {
 cudaStream_t pick(fdr_shard* s, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : s->stream; }
 
-// FDR_SHARD_ROW_CTAS=n: the exchange passes (phase 1 scatter, phase 3 gather) run as at most n persistent CTAs per
-// plane pair, leaving the other SMs to the other pair's column phase in the pair-pipelined driver.  0 = whole grid.
-int shard_row_ctas() {
-    static int v = -1;
-    if (v < 0) {
-        const char* env = getenv("FDR_SHARD_ROW_CTAS");
-        v = (env && atoi(env) > 0) ? atoi(env) : 0;
+// half-plane forms: column owners' slabs and the Nyquist vectors (inside the same allocations) by value in the launch arguments
+void fill_half_peers(const fdr_shard* s, RowPassArgs& r) {
+    for (int i = 0; i < s->world; ++i) {
+        r.hp_peers[i] = s->peer_host[(size_t)i];
+        r.nyq_peers[i] = s->peer_host[(size_t)i] + s->nyq_off;
     }
-    return v;
+    r.hp_shift = ilog2(s->Ch);
+    r.hp_plane = (long long)s->Rp * s->Ch;
+    r.nyq_world = s->world;
+    r.nyq_plane = s->Rp;
 }
 
 int build_wiener(fdr_shard* s) {
     if (s->psf_rows > s->Rp || s->psf_cols > s->Cp)
         return set_error(FDR_E_INVALID, "PSF %dx%d larger than the padded image %dx%d", s->psf_rows, s->psf_cols, s->Rp, s->Cp);
     cudaStream_t st = s->stream;
+    if (s->half) {
+        // Row spectra of the PSF rows, keeping this rank's half-plane columns [rank*Ch, (rank+1)*Ch): the scatter table has one
+        // entry per Ch columns (2*world of them), all NULL but ours.  The Nyquist column comes from its own tiny kernel.
+        RowPassArgs r{};
+        r.n = s->Cp;
+        r.nrows = s->psf_rows;
+        r.npairs = 1;
+        r.in_mode = ROW_IN_PAIR_F32;
+        r.out_mode = ROW_OUT_SCATTER;
+        r.in_f32 = s->psf.p;
+        r.in_unit_stride = (long long)s->psf_rows * s->psf_cols;
+        r.in_row_stride = s->psf_cols;
+        r.channels = 1;
+        r.img_rows = s->psf_rows;
+        r.img_cols = s->psf_cols;
+        r.units_total = 1;
+        r.tw = s->tw_rows;
+        r.peers = s->self_only.p;
+        r.peer_shift = ilog2(s->Ch);
+        r.peer_plane = (long long)s->Rp * s->Ch;
+        r.row0 = 0;
+        FDR_CUDA(launch_row_pass(r, st));
+        float2* nyq0 = s->slab.p + s->nyq_off;  // plane 0's Nyquist vector as scratch
+        FDR_CUDA(launch_psf_nyquist(s->psf.p, s->psf_rows, s->psf_cols, nyq0, st));
+        ColPassArgs c{};
+        c.n = s->Rp;
+        c.pitch = s->Ch;
+        c.npairs = 1;
+        c.mode = COL_MAKE_WIENER;
+        c.rows_valid = s->psf_rows;
+        c.data = s->slab.p;
+        c.cplane = (long long)s->Rp * s->Ch;
+        c.wiener_out = s->wiener.p;
+        c.K = s->K;
+        c.tw = s->tw_cols;
+        if (s->col_split)
+            FDR_CUDA(launch_col_split(c, st, nullptr));
+        else
+            FDR_CUDA(launch_col_pass(c, st));
+        ColPassArgs n = c;
+        n.pitch = 1;
+        n.data = nyq0;
+        n.cplane = s->Rp;
+        n.wiener_out = s->wiener_nyq.p;
+        FDR_CUDA(launch_col_pass(n, st));
+        FDR_CUDA(cudaStreamSynchronize(st));
+        s->have_wiener = true;
+        return FDR_OK;
+    }
     // PSF rows are few (S <= Rp): every rank transforms all of them and keeps its own columns.
     RowPassArgs r{};
     r.n = s->Cp;
@@ -142,9 +208,17 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
     s->rows_local = r1 > s->row0 ? r1 - s->row0 : 0;
     s->npairs = (channels + 1) / 2;
     {
+        const char* hv = getenv("FDR_SHARD_HALF");
+        s->half = !(hv && atoi(hv) == 0) && Cp >= FDR_HALF_MIN_N && s->Cl >= 2 && s->Rl >= 2 && world <= FDR_MAX_PEERS;
+        s->Ch = s->Cl / 2;
+        s->units = s->half ? channels : s->npairs;
+        const char* rc = getenv("FDR_SHARD_ROW_CTAS");
+        s->row_ctas = (rc && atoi(rc) > 0) ? atoi(rc) : 0;
+    }
+    {
         ColPassArgs probe{};
         probe.n = Rp;
-        probe.pitch = Cp / world;
+        probe.pitch = s->half ? s->Ch : Cp / world;
         probe.mode = COL_WIENER;
         const char* cs = getenv("FDR_COL_SPLIT");
         s->col_split = col_split_applicable(probe) && !(cs && atoi(cs) == 0);
@@ -154,18 +228,25 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
     if (e == cudaSuccess) e = get_twiddles(Rp, &s->tw_cols);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "shard setup: %s", cudaGetErrorString(e));
-    if (rc == FDR_OK) rc = s->slab.ensure((size_t)s->npairs * Rp * s->Cl);
-    if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Cl);
+    if (s->half) {
+        s->nyq_off = (size_t)channels * Rp * s->Ch;
+        if (rc == FDR_OK) rc = s->slab.ensure(s->nyq_off + (size_t)channels * Rp);
+        if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Ch);
+        if (rc == FDR_OK) rc = s->wiener_nyq.ensure((size_t)Rp);
+    } else {
+        if (rc == FDR_OK) rc = s->slab.ensure((size_t)s->npairs * Rp * s->Cl);
+        if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Cl);
+    }
     if (rc == FDR_OK) rc = s->raw.ensure((size_t)channels * (s->rows_local > 0 ? s->rows_local : 1) * cols);
     if (rc == FDR_OK) rc = s->mm.ensure((size_t)channels * 2 * FDR_MINMAX_SLOTS);
     if (rc == FDR_OK) rc = s->mmf.ensure((size_t)channels * 2);
     if (rc == FDR_OK) rc = s->ss.ensure((size_t)channels);
     if (rc == FDR_OK) rc = s->peers.ensure((size_t)world);
-    if (rc == FDR_OK) rc = s->self_only.ensure((size_t)world);
+    if (rc == FDR_OK) rc = s->self_only.ensure((size_t)2 * world);
     if (rc == FDR_OK) {
-        std::vector<float2*> tbl((size_t)world, nullptr);
+        std::vector<float2*> tbl((size_t)2 * world, nullptr);  // (half-plane Wiener build: one entry per Cl/2 columns)
         tbl[(size_t)rank] = s->slab.p;
-        e = cudaMemcpy(s->self_only.p, tbl.data(), sizeof(float2*) * world, cudaMemcpyHostToDevice);
+        e = cudaMemcpy(s->self_only.p, tbl.data(), sizeof(float2*) * 2 * world, cudaMemcpyHostToDevice);
         if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "peer table: %s", cudaGetErrorString(e));
     }
     if (rc != FDR_OK) {
@@ -182,6 +263,7 @@ FDR_API int fdr_shard_destroy(fdr_shard* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->slab.release();
     s->wiener.release();
+    s->wiener_nyq.release();
     s->raw.release();
     s->mm.release();
     s->mmf.release();
@@ -243,6 +325,7 @@ FDR_API int fdr_shard_set_peers(fdr_shard* s, void* const* slabs) {
         if (!tbl[(size_t)i]) return set_error(FDR_E_INVALID, "peer %d slab is NULL", i);
     }
     FDR_CUDA(cudaMemcpy(s->peers.p, tbl.data(), sizeof(float2*) * s->world, cudaMemcpyHostToDevice));
+    s->peer_host = tbl;
     s->have_peers = true;
     return FDR_OK;
 }
@@ -271,14 +354,14 @@ FDR_API int fdr_shard_set_psf_host(fdr_shard* s, const float* psf, int psf_rows,
 // phase 1: rows forward + scatter to the owners of the columns.  d_in_rows: this rank's rows of
 // the image, interleaved u8 [rows_local][W][C].
 static int check_pairs(const fdr_shard* s, int pair_first, int pair_count) {
-    if (pair_first < 0 || pair_count < 1 || pair_first + pair_count > s->npairs)
-        return set_error(FDR_E_INVALID, "pair range [%d, +%d) outside 0..%d", pair_first, pair_count, s->npairs);
+    if (pair_first < 0 || pair_count < 1 || pair_first + pair_count > s->units)
+        return set_error(FDR_E_INVALID, "unit range [%d, +%d) outside 0..%d", pair_first, pair_count, s->units);
     return FDR_OK;
 }
 
 FDR_API int fdr_shard_phase1_rows(fdr_shard* s, const void* d_in_rows_u8, void* stream) {
     if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
-    return fdr_shard_phase1_pairs(s, d_in_rows_u8, 0, s->npairs, stream);
+    return fdr_shard_phase1_pairs(s, d_in_rows_u8, 0, s->units, stream);
 }
 
 FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int pair_first, int pair_count, void* stream) {
@@ -288,15 +371,41 @@ FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int p
     FDR_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = pick(s, stream);
     if (pair_first == 0) s->launches = 0;
-    {   // extrema of the planes these pairs carry
-        const int u0 = 2 * pair_first;
-        int nu = 2 * pair_count;
+    {   // extrema of the planes these units carry
+        const int per = s->half ? 1 : 2;
+        const int u0 = per * pair_first;
+        int nu = per * pair_count;
         if (u0 + nu > s->C) nu = s->C - u0;
         FDR_CUDA(launch_minmax_reset(s->mm.p + (size_t)2 * FDR_MINMAX_SLOTS * u0, nu, st));
         s->launches += 1;
     }
     if (s->rows_local == 0) return FDR_OK;  // slab entirely inside the zero padding
     if (!d_in_rows_u8) return set_error(FDR_E_INVALID, "input rows are NULL");
+    if (s->half) {
+        RowPassArgs r{};
+        r.n = s->Cp;
+        r.pair_dist = (s->rows_local + 1) / 2;
+        r.nrows = r.pair_dist;
+        r.npairs = pair_count;
+        r.pair_base = pair_first;
+        r.in_mode = ROW_IN_ROWS2_U8;
+        r.out_mode = ROW_OUT_HALF;
+        r.in_u8 = static_cast<const uint8_t*>(d_in_rows_u8);
+        r.channels = s->C;
+        r.img_rows = s->rows_local;
+        r.img_cols = s->W;
+        r.rows_in = s->rows_local;
+        r.hp_rows_store = s->H;
+        r.unit_base = 0;
+        r.units_total = s->C;
+        r.tw = s->tw_rows;
+        fill_half_peers(s, r);
+        r.row0 = s->row0;
+        r.max_ctas = s->row_ctas;
+        FDR_CUDA(launch_row_pass(r, st));
+        s->launches += 1;
+        return FDR_OK;
+    }
     RowPassArgs r{};
     r.n = s->Cp;
     r.nrows = s->rows_local;
@@ -315,7 +424,7 @@ FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int p
     r.peer_shift = ilog2(s->Cl);
     r.peer_plane = (long long)s->Rp * s->Cl;
     r.row0 = s->row0;
-    r.max_ctas = shard_row_ctas();
+    r.max_ctas = s->row_ctas;
     FDR_CUDA(launch_row_pass(r, st));
     s->launches += 1;
     return FDR_OK;
@@ -324,7 +433,7 @@ FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int p
 // phase 2: columns of the local slab, in place (FFT, Wiener factor, inverse FFT).
 FDR_API int fdr_shard_phase2_cols(fdr_shard* s, void* stream) {
     if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
-    return fdr_shard_phase2_pairs(s, 0, s->npairs, stream);
+    return fdr_shard_phase2_pairs(s, 0, s->units, stream);
 }
 
 FDR_API int fdr_shard_phase2_pairs(fdr_shard* s, int pair_first, int pair_count, void* stream) {
@@ -333,13 +442,13 @@ FDR_API int fdr_shard_phase2_pairs(fdr_shard* s, int pair_first, int pair_count,
     FDR_CUDA(cudaSetDevice(s->device));
     ColPassArgs c{};
     c.n = s->Rp;
-    c.pitch = s->Cl;
+    c.pitch = s->half ? s->Ch : s->Cl;
     c.npairs = pair_count;
     c.pair_base = pair_first;
     c.mode = COL_WIENER;
     c.rows_valid = s->H;
     c.data = s->slab.p;
-    c.cplane = (long long)s->Rp * s->Cl;
+    c.cplane = (long long)s->Rp * c.pitch;
     c.wiener = s->wiener.p;
     c.K = s->K;
     c.tw = s->tw_cols;
@@ -351,13 +460,29 @@ FDR_API int fdr_shard_phase2_pairs(fdr_shard* s, int pair_first, int pair_count,
         FDR_CUDA(launch_col_pass(c, pick(s, stream)));
         s->launches += 1;
     }
+    if (s->half) {
+        // the Nyquist columns this rank owns: one more column of the same problem each (plain column kernel, natural order)
+        for (int u = pair_first; u < pair_first + pair_count; ++u) {
+            if (u % s->world != s->rank) continue;
+            ColPassArgs n = c;
+            n.pitch = 1;
+            n.npairs = 1;
+            n.pair_base = 0;
+            n.data = s->slab.p + s->nyq_off + (size_t)u * s->Rp;
+            n.cplane = s->Rp;
+            n.wiener = s->wiener_nyq.p;
+            n.wiener_tiled = nullptr;
+            FDR_CUDA(launch_col_pass(n, pick(s, stream)));
+            s->launches += 1;
+        }
+    }
     return FDR_OK;
 }
 
 // phase 3: gather the local padded rows from every slab, inverse rows, min/max of the local part.
 FDR_API int fdr_shard_phase3_rows(fdr_shard* s, void* stream) {
     if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
-    return fdr_shard_phase3_pairs(s, 0, s->npairs, stream);
+    return fdr_shard_phase3_pairs(s, 0, s->units, stream);
 }
 
 FDR_API int fdr_shard_phase3_pairs(fdr_shard* s, int pair_first, int pair_count, void* stream) {
@@ -367,11 +492,13 @@ FDR_API int fdr_shard_phase3_pairs(fdr_shard* s, int pair_first, int pair_count,
     cudaStream_t st = pick(s, stream);
     RowPassArgs r{};
     r.n = s->Cp;
-    r.nrows = s->Rl;
+    r.nrows = s->half ? s->Rl / 2 : s->Rl;
     r.npairs = pair_count;
     r.pair_base = pair_first;
-    r.in_mode = ROW_IN_GATHER;
-    r.out_mode = ROW_OUT_REAL_PAIR;
+    r.in_mode = s->half ? ROW_IN_HALF : ROW_IN_GATHER;
+    r.out_mode = s->half ? ROW_OUT_REAL_ROWS2 : ROW_OUT_REAL_PAIR;
+    r.pair_dist = s->Rl / 2;
+    if (s->half) fill_half_peers(s, r);
     r.unit_base = 0;
     r.units_total = s->C;
     r.raw = s->raw.p;
@@ -385,13 +512,14 @@ FDR_API int fdr_shard_phase3_pairs(fdr_shard* s, int pair_first, int pair_count,
     r.peer_shift = ilog2(s->Cl);
     r.peer_plane = (long long)s->Rp * s->Cl;
     r.row0 = s->row0;
-    r.max_ctas = shard_row_ctas();
+    r.max_ctas = s->row_ctas;
     FDR_CUDA(launch_row_pass(r, st));
     {
-        const int u0 = 2 * pair_first;
-        int nu = 2 * pair_count;
+        const int per = s->half ? 1 : 2;
+        const int u0 = per * pair_first;
+        int nu = per * pair_count;
         if (u0 + nu > s->C) nu = s->C - u0;
-        FDR_CUDA(launch_minmax_decode(s->mm.p + (size_t)2 * FDR_MINMAX_SLOTS * u0, s->mmf.p + 2 * u0, nu, st));
+        FDR_CUDA(launch_minmax_decode(s->mm.p + (size_t)2 * FDR_MINMAX_SLOTS * u0, s->mmf.p + 2 * u0, nu, s->minmax_neg, st));
     }
     s->launches += 2;
     return FDR_OK;
@@ -410,7 +538,7 @@ FDR_API int fdr_shard_phase4_pack(fdr_shard* s, void* d_out_rows_u8, void* strea
     if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
     FDR_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = pick(s, stream);
-    FDR_CUDA(launch_scale_shift_from_f32(s->mmf.p, s->ss.p, s->C, st));
+    FDR_CUDA(launch_scale_shift_from_f32(s->mmf.p, s->ss.p, s->C, s->minmax_neg, st));
     s->launches += 1;
     if (s->rows_local == 0) return FDR_OK;
     if (!d_out_rows_u8) return set_error(FDR_E_INVALID, "output rows are NULL");
@@ -422,7 +550,29 @@ FDR_API int fdr_shard_phase4_pack(fdr_shard* s, void* d_out_rows_u8, void* strea
 
 FDR_API int fdr_shard_pair_count(const fdr_shard* s, int* pairs) {
     if (!s || !pairs) return set_error(FDR_E_INVALID, "bad arguments");
-    *pairs = s->npairs;
+    *pairs = s->units;
+    return FDR_OK;
+}
+
+// Exchange passes (phase 1 scatter, phase 3 gather) as at most `ctas` persistent CTAs per unit (0 = the whole grid), so
+// that another unit's column phase finds free SMs while this one waits on NVLink.  Default: FDR_SHARD_ROW_CTAS or 0.
+FDR_API int fdr_shard_set_row_ctas(fdr_shard* s, int ctas) {
+    if (!s || ctas < 0) return set_error(FDR_E_INVALID, "bad arguments");
+    s->row_ctas = ctas;
+    return FDR_OK;
+}
+
+// enabled: the device min/max vector (fdr_shard_minmax_device) holds (min, -max) per plane, so ONE all-reduce(MIN) over the
+// whole [channels][2] vector yields the global extrema; phase 4 undoes the sign.
+FDR_API int fdr_shard_set_minmax_negated(fdr_shard* s, int enabled) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    s->minmax_neg = enabled != 0;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_half_plane(const fdr_shard* s, int* enabled) {
+    if (!s || !enabled) return set_error(FDR_E_INVALID, "bad arguments");
+    *enabled = s->half ? 1 : 0;
     return FDR_OK;
 }
 

@@ -56,6 +56,7 @@ def lib():
             "fdr_plan_padded_size": [vp, C.POINTER(i), C.POINTER(i)],
             "fdr_plan_set_chunk_images": [vp, i],
             "fdr_plan_set_white_balance": [vp, i],
+            "fdr_plan_half_plane": [vp, C.POINTER(i)],
             "fdr_white_balance_pack_host": [C.POINTER(_fp), C.POINTER(_fp), i, i, vp],
             "fdr_plan_set_psf_host": [vp, _fp, i, i, sz, f],
             "fdr_plan_set_psf_motion": [vp, i, d, f],
@@ -96,6 +97,9 @@ def lib():
             "fdr_shard_phase2_pairs": [vp, i, i, vp],
             "fdr_shard_phase3_pairs": [vp, i, i, vp],
             "fdr_shard_pair_count": [vp, C.POINTER(i)],
+            "fdr_shard_half_plane": [vp, C.POINTER(i)],
+            "fdr_shard_set_row_ctas": [vp, i],
+            "fdr_shard_set_minmax_negated": [vp, i],
             "fdr_shard_minmax_device": [vp, pp],
             "fdr_shard_phase4_pack": [vp, vp, vp],
             "fdr_shard_last_launch_count": [vp, C.POINTER(ll)],
@@ -181,6 +185,12 @@ class Plan:
 
     def set_white_balance(self, on=True):
         _check(lib().fdr_plan_set_white_balance(self.h, int(on)))
+
+    @property
+    def half_plane(self):
+        v = C.c_int(0)
+        _check(lib().fdr_plan_half_plane(self.h, C.byref(v)))
+        return bool(v.value)
 
     def set_psf(self, psf, K=0.01):
         psf = _f32(psf)
@@ -331,6 +341,19 @@ class Shard:
         n = C.c_int(0)
         _check(lib().fdr_shard_pair_count(self.h, C.byref(n)))
         return n.value
+
+    @property
+    def half_plane(self):
+        v = C.c_int(0)
+        _check(lib().fdr_shard_half_plane(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def set_row_ctas(self, n):
+        _check(lib().fdr_shard_set_row_ctas(self.h, int(n)))
+
+    def set_minmax_negated(self, on=True):
+        _check(lib().fdr_shard_set_minmax_negated(self.h, int(on)))
+        self.minmax_negated = bool(on)
 
     def phase1(self, d_in_rows, stream=0, pair=None):
         if pair is None:

@@ -50,7 +50,13 @@ def device_tensor(ptr, shape, device, typestr="<f4"):
 
 class ShardedRestorer:
     """Per-rank driver of the row-sharded restoration.  `backend` is an fdr.Shard (CUDA) or any
-    object with the same phase API (the CPU gloo test passes a numpy stand-in)."""
+    object with the same phase API (the CPU gloo test passes a numpy stand-in).
+
+    Pipeline units: a backend splits the image into `npairs` independent units (plane pairs, or single
+    planes in half-plane mode).  With more than one unit and a CUDA backend the units run on their own
+    streams -- phase 1 | barrier | phase 2 | barrier | phase 3 per unit -- so that unit u's NVLink-bound
+    row phases overlap unit u-1's HBM-bound column phase; every rank issues the collectives in the same
+    order.  The reference runs its channels strictly one after the other (mpi.cpp:95-111)."""
 
     def __init__(self, backend, group=None, device=None):
         self.b = backend
@@ -68,7 +74,8 @@ class ShardedRestorer:
         backend.set_peers_from_handles(handles)
         self._mm = backend.minmax_tensor(device)      # [channels][2] view, all-reduced in place
         self._flag = torch.zeros(1, dtype=torch.float32, device=self._mm.device)
-        self._side = None                             # side streams + flags of the pair pipeline
+        self._side = None                             # side streams + flags of the unit pipeline
+        self._cuda = self._mm.is_cuda
 
     def set_psf_motion(self, length, angle_deg, K):
         """PSF + Wiener factor on every rank, then a cross-rank fence: the build uses the rank's column slab as
@@ -91,55 +98,66 @@ class ShardedRestorer:
         if self.world > 1:
             dist.all_reduce(self._flag if flag is None else flag, group=self.group)
 
-    def _restore_rows_pair_pipeline(self, d_in_rows, d_out_rows, stream):
-        """Two plane pairs on two side streams: pair 1's NVLink-bound row phase overlaps pair 0's
-        HBM-bound column phase (and so on).  Every rank issues the collectives in the same order."""
+    def _reduce_minmax(self):
+        """Global extrema of every padded plane (also the barrier that frees the slabs for the next image)."""
+        if self.world <= 1:
+            return
+        if getattr(self.b, "minmax_negated", False):
+            dist.all_reduce(self._mm, op=dist.ReduceOp.MIN, group=self.group)  # (min, -max): one collective
+            return
+        mn = self._mm[:, 0].contiguous()
+        mx = self._mm[:, 1].contiguous()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        self._mm[:, 0].copy_(mn)
+        self._mm[:, 1].copy_(mx)
+
+    def _restore_rows_unit_pipeline(self, d_in_rows, main):
+        """Every unit on its own side stream, phases interleaved across units in issue order."""
         b = self.b
-        main = torch.cuda.current_stream()
-        if self._side is None:
+        n = b.npairs
+        if self._side is None or len(self._side) != n:
             dev = self._mm.device
-            self._side = [(torch.cuda.Stream(device=dev), torch.zeros(1, dtype=torch.float32, device=dev)) for _ in range(2)]
+            self._side = [(torch.cuda.Stream(device=dev), torch.zeros(1, dtype=torch.float32, device=dev)) for _ in range(n)]
         for st, _ in self._side:
             st.wait_stream(main)
         for phase in (1, 2, 3):
-            for pair, (st, flag) in enumerate(self._side):
+            for unit, (st, flag) in enumerate(self._side):
                 with torch.cuda.stream(st):
                     if phase == 1:
-                        b.phase1(d_in_rows, st.cuda_stream, pair=pair)
+                        b.phase1(d_in_rows, st.cuda_stream, pair=unit)
                     elif phase == 2:
-                        b.phase2(st.cuda_stream, pair=pair)
+                        b.phase2(st.cuda_stream, pair=unit)
                     else:
-                        b.phase3(st.cuda_stream, pair=pair)
+                        b.phase3(st.cuda_stream, pair=unit)
                     if phase < 3:
                         self.barrier(flag)
         for st, _ in self._side:
             main.wait_stream(st)
 
-    def restore_rows(self, d_in_rows, d_out_rows, stream=0, pipeline_pairs=True):
+    def restore_rows(self, d_in_rows, d_out_rows, stream=None, pipeline_pairs=True):
+        """stream: raw CUDA stream handle of torch's CURRENT stream (default: looked up).  The barriers and the min/max
+        all-reduce are torch.distributed calls, which order themselves against the current stream only, so the phases
+        must run on that same stream; any other handle (including 0, the legacy stream) is rejected."""
         b = self.b
-        if (pipeline_pairs and self.world > 1 and getattr(b, "supports_pair_pipeline", False) and b.npairs == 2
-                and torch.cuda.current_stream().cuda_stream == stream):
-            self._restore_rows_pair_pipeline(d_in_rows, d_out_rows, stream)
-            mn = self._mm[:, 0].contiguous()
-            mx = self._mm[:, 1].contiguous()
-            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-            self._mm[:, 0].copy_(mn)
-            self._mm[:, 1].copy_(mx)
-            b.phase4(d_out_rows, stream)
-            return
-        b.phase1(d_in_rows, stream)
-        self.barrier()                      # every slab has received all its columns
-        b.phase2(stream)
-        self.barrier()                      # every slab holds the filtered, column-inverted data
-        b.phase3(stream)
-        if self.world > 1:                  # global extrema of every padded plane (also the barrier
-            mn = self._mm[:, 0].contiguous()  # that frees the slabs for the next image)
-            mx = self._mm[:, 1].contiguous()
-            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
-            self._mm[:, 0].copy_(mn)
-            self._mm[:, 1].copy_(mx)
+        if self._cuda:
+            cur = torch.cuda.current_stream(self._mm.device)
+            if stream is None:
+                stream = cur.cuda_stream
+            elif stream != cur.cuda_stream:
+                raise ValueError("restore_rows: `stream` must be torch's current stream (set it with torch.cuda.stream / "
+                                 "set_stream); the cross-rank barriers are ordered against that stream only")
+        elif stream is None:
+            stream = 0
+        if (pipeline_pairs and self._cuda and self.world > 1 and getattr(b, "supports_pair_pipeline", False) and b.npairs >= 2):
+            self._restore_rows_unit_pipeline(d_in_rows, cur)
+        else:
+            b.phase1(d_in_rows, stream)
+            self.barrier()                      # every slab has received all its columns
+            b.phase2(stream)
+            self.barrier()                      # every slab holds the filtered, column-inverted data
+            b.phase3(stream)
+        self._reduce_minmax()
         b.phase4(d_out_rows, stream)
 
 
@@ -148,4 +166,5 @@ def cuda_shard_backend(fdr, rows, cols, channels, rank, world, device_index):
     sh = fdr.Shard(rows, cols, channels, rank, world, device_index)
     sh.minmax_tensor = lambda device: device_tensor(sh.minmax_ptr(), (channels, 2), device or torch.device("cuda", device_index))
     sh.supports_pair_pipeline = True
+    sh.set_minmax_negated(True)   # one all-reduce(MIN) over (min, -max) instead of two collectives + four copies
     return sh

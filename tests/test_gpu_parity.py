@@ -343,3 +343,103 @@ def test_kernel_timing_api(gpu, oracle):
         kt = p.kernel_timing()
         assert p.last_launch_count() == 6
     assert all(kt[k]["launches"] == 1 and kt[k]["ms"] > 0 and kt[k]["bytes"] > 0 for k in kt)
+
+
+HALF_CASES = [(48, 80, 9, 30.0), (64, 64, 5, 10.0), (100, 200, 21, 45.0), (7, 70, 3, 20.0), (2, 64, 1, 0.0), (3, 33, 1, 0.0),
+              (256, 256, 50, 30.0), (330, 640, 40, 45.0), (17, 300, 15, 123.4), (782, 1920, 50, 30.0),
+              (8192, 96, 9, 30.0), (5000, 100, 21, 45.0), (16384, 80, 5, 10.0), (9000, 130, 3, 20.0),
+              (2048, 96, 9, 30.0), (1100, 130, 5, 10.0), (4096, 200, 9, 30.0), (1024, 2048, 9, 30.0)]
+
+
+@pytest.mark.parametrize("H,W,S,ang", HALF_CASES)
+def test_half_plane_lone_plane_parity(gpu, oracle, monkeypatch, H, W, S, ang):
+    """An odd plane count sends the last plane through the half-plane path (two rows of the plane per complex row
+    transform, Hermitian half spectrum + Nyquist column; passes.h).  Forced on for every size here
+    (FDR_HALF_MIN_PIXELS=0); gates are the oracle's, for 3 planes (one pair + the lone plane) and for 1 plane."""
+    monkeypatch.setenv("FDR_HALF_MIN_PIXELS", "0")
+    monkeypatch.setenv("FDR_HALF", "1")
+    rng = np.random.default_rng(H * 1000 + W + 1)
+    planes = [rng.random((H, W), dtype=np.float32) for _ in range(3)]
+    psf = oracle.port().motion_psf(S, ang)
+    with gpu.Plan(H, W, 3) as p:
+        p.set_psf(psf, K)
+        expect_half = p.padded[1] >= 64 and p.padded[0] >= 2
+        assert p.half_plane == expect_half
+        outs = p.restore_planes(planes)
+        mm = p.last_minmax(3)
+        lone_only = p.restore_planes([planes[2]])[0]
+    want_u8, want = oracle.restore_image_u8(planes, psf, K)
+    res = oracle.port().wiener_deblur(oracle.pad_pow2(planes[2]), psf, K, want=("norm", "raw"))
+    lo, hi = res["minmax"]
+    assert abs(mm[2, 0] - lo) <= 1e-4 * (hi - lo) and abs(mm[2, 1] - hi) <= 1e-4 * (hi - lo)
+    for a, b in zip(outs, want):
+        assert np.abs(a - b).max() < 1e-4
+    assert np.abs(lone_only - want[2]).max() < 1e-4
+    got_u8 = np.stack([oracle.port().pack_u8(o) for o in outs], -1)
+    if H * W >= 1000:
+        check_u8(got_u8, want_u8)
+    else:
+        assert np.abs(got_u8.astype(int) - want_u8.astype(int)).max() <= 1
+
+
+def test_half_plane_u8_images_and_chunks(gpu, oracle, monkeypatch):
+    """u8 image entry point with the half-plane path forced on: one image per chunk (3 planes: a pair + the lone plane)
+    against two images per chunk (6 planes: pairs only) -- the two arithmetic paths agree to <= 1 LSB -- and the oracle."""
+    monkeypatch.setenv("FDR_HALF_MIN_PIXELS", "0")
+    H, W, n = 200, 300, 4
+    imgs = np.stack([np.transpose(oracle.synth_image_u8(7, i, H, W), (1, 2, 0)) for i in range(n)])
+    psf = oracle.port().motion_psf(9, 30.0)
+    outs = []
+    for chunk in (1, 2):
+        with gpu.Plan(H, W, 3, max_images=n) as p:
+            p.set_psf(psf, K)
+            p.set_chunk_images(chunk)
+            assert p.half_plane
+            outs.append(p.restore_images_u8(imgs))
+    ex, off1, worse = u8_gate(outs[0], outs[1])
+    assert worse == 0 and off1 <= 2e-3 * outs[0].size, (ex, off1, worse)
+    for i in (0, n - 1):
+        planes = [imgs[i, :, :, c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(3)]
+        want, _ = oracle.restore_image_u8(planes, psf, K)
+        check_u8(outs[0][i], want)
+
+
+def test_plan_calls_on_two_streams_are_ordered(gpu, oracle):
+    """One workspace per plan: device restores issued on two different streams (and a PSF rebuild in between) are ordered
+    through the plan's event instead of racing (include/fdr_b200.h, "streams")."""
+    torch = pytest.importorskip("torch")
+    H = W = 1024
+    dev = torch.device("cuda", 0)
+    img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(7, 1, H, W), (1, 2, 0)))
+    d_in = torch.from_numpy(img).to(dev)
+    outs = [torch.zeros_like(d_in) for _ in range(3)]
+    sts = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    with gpu.Plan(H, W, 3) as p:
+        p.set_psf_motion(9, 30.0, K)
+        p.restore_images_device_u8(d_in.data_ptr(), outs[0].data_ptr(), 1, sts[0].cuda_stream)
+        p.restore_images_device_u8(d_in.data_ptr(), outs[1].data_ptr(), 1, sts[1].cuda_stream)
+        p.set_psf_motion(9, 30.0, K)  # rebuilds the factor through the shared workspace
+        p.restore_images_device_u8(d_in.data_ptr(), outs[2].data_ptr(), 1, sts[0].cuda_stream)
+        torch.cuda.synchronize()
+    a, b, c = (o.cpu().numpy() for o in outs)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    planes = [img[:, :, k].astype(np.float32) * np.float32(1.0 / 255.0) for k in range(3)]
+    want, _ = oracle.restore_image_u8(planes, oracle.port().motion_psf(9, 30.0), K)
+    check_u8(a, want)
+
+
+def test_many_tiny_images_grid_cap(gpu, oracle):
+    """More plane pairs than gridDim.y allows in one launch: the chunk size is capped (65534 planes)."""
+    H, W, n = 4, 4, 44000  # 132000 planes
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    psf = np.zeros((3, 3), np.float32)
+    psf[1, :] = 1.0 / 3
+    with gpu.Plan(H, W, 3, max_images=n) as p:
+        p.set_psf(psf, K)
+        out = p.restore_images_u8(imgs)
+    for i in (0, 21844, 21845, n - 1):
+        planes = [imgs[i, :, :, c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(3)]
+        want, _ = oracle.restore_image_u8(planes, psf, K)
+        assert np.abs(out[i].astype(int) - want.astype(int)).max() <= 1

@@ -2,6 +2,8 @@
 process on ONE device (peer pointers are plain device pointers), the phases of all ranks run in
 order with a device synchronise where the real run has a cross-rank barrier.  The result must
 equal the unsharded plan and pass the oracle gates."""
+import os
+
 import numpy as np
 import pytest
 
@@ -11,19 +13,53 @@ pytestmark = pytest.mark.gpu
 K = 0.01
 
 
-def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang):
+def make_shards(gpu, H, W, C, world, half):
+    """half: True / False select the half-plane / plane-pair form (FDR_SHARD_HALF, read at creation)."""
+    old = os.environ.get("FDR_SHARD_HALF")
+    os.environ["FDR_SHARD_HALF"] = "1" if half else "0"
+    try:
+        return [gpu.Shard(H, W, C, g, world, 0) for g in range(world)]
+    finally:
+        if old is None:
+            del os.environ["FDR_SHARD_HALF"]
+        else:
+            os.environ["FDR_SHARD_HALF"] = old
+
+
+def single_gpu(gpu, img, psf_len, psf_ang, half):
+    """Unsharded plan; half=False keeps its odd plane on the plane-pair path (bit-identical to pair-mode shards)."""
+    old = os.environ.get("FDR_HALF")
+    os.environ["FDR_HALF"] = "1" if half else "0"
+    try:
+        with gpu.Plan(img.shape[0], img.shape[1], img.shape[2]) as p:
+            p.set_psf_motion(psf_len, psf_ang, K)
+            return p.restore_images_u8(img[None])[0]
+    finally:
+        if old is None:
+            del os.environ["FDR_HALF"]
+        else:
+            os.environ["FDR_HALF"] = old
+
+
+def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang, half=False, row_ctas=0, negated=False):
     H, W, C = images_hwc.shape
     dev = torch.device("cuda", 0)
     d_in = torch.from_numpy(images_hwc).to(dev)
     d_out = torch.zeros_like(d_in)
     dist_mod = _load("fdr_dist", PKG + "/fdr_dist.py")
-    shards = [gpu.Shard(H, W, C, g, world, 0) for g in range(world)]
+    shards = make_shards(gpu, H, W, C, world, half)
     try:
         slabs = [s.local_slab()[0] for s in shards]
         for g, s in enumerate(shards):
             assert (s.first_row, s.n_rows) == dist_mod.row_slab(g, world, H)
             s.set_peers(slabs)
             s.set_psf_motion(psf_len, psf_ang, K)
+            if row_ctas:
+                s.set_row_ctas(row_ctas)
+            if negated:
+                s.set_minmax_negated(True)
+        half_on = shards[0].half_plane
+        assert shards[0].npairs == (C if half_on else (C + 1) // 2)
         stream = torch.cuda.Stream(device=dev)
         sh = stream.cuda_stream
         rowbytes = W * C
@@ -38,10 +74,15 @@ def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang):
         torch.cuda.synchronize()
         mms = [dist_mod.device_tensor(s.minmax_ptr(), (C, 2), dev) for s in shards]
         allmm = torch.stack(mms)
-        gmin, gmax = allmm[:, :, 0].min(0).values, allmm[:, :, 1].max(0).values
-        for t in mms:
-            t[:, 0] = gmin
-            t[:, 1] = gmax
+        if negated:   # (min, -max): the all-reduce(MIN) of the real driver
+            g = allmm.min(0).values
+            for t in mms:
+                t.copy_(g)
+        else:
+            gmin, gmax = allmm[:, :, 0].min(0).values, allmm[:, :, 1].max(0).values
+            for t in mms:
+                t[:, 0] = gmin
+                t[:, 1] = gmax
         torch.cuda.synchronize()
         for s in shards:
             s.phase4(d_out.data_ptr() + s.first_row * rowbytes, sh)
@@ -53,47 +94,80 @@ def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang):
             s.close()
 
 
+def oracle_gate(oracle, img, got, psf_len, psf_ang):
+    planes = [img[:, :, c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(img.shape[2])]
+    want, _ = oracle.restore_image_u8(planes, oracle.port().motion_psf(psf_len, psf_ang), K)
+    exact, off1, worse = u8_gate(got, want)
+    assert worse == 0 and (exact + off1) / got.size >= 0.999, (exact, off1, worse)
+
+
 @pytest.mark.parametrize("H,W,world", [(200, 320, 2), (200, 320, 4), (256, 512, 8), (64, 1024, 2), (1000, 40, 4), (33, 70, 8),
                                        (8192, 64, 2), (16384, 128, 8)])
 def test_sharded_equals_single_gpu_and_oracle(gpu, oracle, H, W, world):
+    """Plane-pair form (FDR_SHARD_HALF=0): bit-identical to the unsharded plan on the same path."""
     torch = pytest.importorskip("torch")
     img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 0, H, W), (1, 2, 0)))
-    got, launches = run_emulated(gpu, torch, img, world, 9, 30.0)
+    got, launches = run_emulated(gpu, torch, img, world, 9, 30.0, half=False)
     assert launches > 0
-    with gpu.Plan(H, W, 3) as p:
-        p.set_psf_motion(9, 30.0, K)
-        single = p.restore_images_u8(img[None])[0]
+    single = single_gpu(gpu, img, 9, 30.0, half=False)
     assert np.array_equal(got, single), u8_gate(got, single)
-    planes = [img[:, :, c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(3)]
-    want, _ = oracle.restore_image_u8(planes, oracle.port().motion_psf(9, 30.0), K)
-    exact, off1, worse = u8_gate(got, want)
-    assert worse == 0 and (exact + off1) / got.size >= 0.999
+    oracle_gate(oracle, img, got, 9, 30.0)
 
 
-@pytest.mark.parametrize("H,W,world", [(192, 256, 2), (8192, 64, 2), (16384, 4096, 2)])
-def test_sharded_per_pair_phases(gpu, oracle, H, W, world):
-    """fdr_shard_phase*_pairs: running the two plane pairs separately, on two concurrent streams (as
-    the pipelined driver does), gives the same bytes as the all-pairs phases -- also for the long-column
+@pytest.mark.parametrize("H,W,world,C", [(200, 320, 2, 3), (200, 320, 4, 3), (256, 512, 8, 3), (64, 1024, 2, 3), (1000, 70, 4, 3),
+                                         (33, 70, 8, 3), (8192, 128, 2, 3), (16384, 256, 8, 3), (5000, 256, 4, 3),
+                                         (300, 500, 2, 1), (300, 500, 4, 4), (2048, 512, 2, 3), (4096, 2048, 4, 3)])
+def test_sharded_half_plane_mode(gpu, oracle, H, W, world, C):
+    """Half-plane form (the default): every plane its own unit, Hermitian half spectra + Nyquist vector through the exchange.
+    Oracle gates, and against the plane-pair form (same data, other arithmetic: differences are rounding, <= 1 LSB)."""
+    torch = pytest.importorskip("torch")
+    img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 2, H, W, channels=C), (1, 2, 0)))
+    got, launches = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, negated=True)
+    assert launches > 0
+    pair, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=False)
+    exact, off1, worse = u8_gate(got, pair)
+    assert worse == 0 and off1 <= 2e-3 * got.size, (exact, off1, worse)
+    if H * W <= 1 << 22:
+        oracle_gate(oracle, img, got, 9, 30.0)
+
+
+def test_sharded_half_plane_persistent_row_ctas(gpu, oracle):
+    """fdr_shard_set_row_ctas: the exchange passes as a few persistent CTAs give the same bytes."""
+    torch = pytest.importorskip("torch")
+    H, W = 2048, 2048
+    img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 3, H, W), (1, 2, 0)))
+    want, _ = run_emulated(gpu, torch, img, 4, 9, 30.0, half=True)
+    for ctas in (7, 40):
+        got, _ = run_emulated(gpu, torch, img, 4, 9, 30.0, half=True, row_ctas=ctas)
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("H,W,world,half", [(192, 256, 2, False), (8192, 64, 2, False), (16384, 4096, 2, False),
+                                            (192, 256, 2, True), (8192, 128, 2, True), (16384, 4096, 2, True)])
+def test_sharded_per_pair_phases(gpu, oracle, H, W, world, half):
+    """fdr_shard_phase*_pairs: running the units (plane pairs, or planes in half-plane mode) separately, on concurrent
+    streams (as the pipelined driver does), gives the same bytes as the all-units phases -- also for the long-column
     schemes (8192 / 16384 rows) at a realistic slab width."""
     torch = pytest.importorskip("torch")
     img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 1, H, W), (1, 2, 0)))
-    want, _ = run_emulated(gpu, torch, img, world, 9, 30.0)
+    want, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=half)
     dev = torch.device("cuda", 0)
     d_in = torch.from_numpy(img).to(dev)
     d_out = torch.zeros_like(d_in)
     dist_mod = _load("fdr_dist", PKG + "/fdr_dist.py")
-    shards = [gpu.Shard(H, W, 3, g, world, 0) for g in range(world)]
+    shards = make_shards(gpu, H, W, 3, world, half)
     try:
         slabs = [s.local_slab()[0] for s in shards]
+        nunits = 3 if half else 2
         for s in shards:
-            assert s.npairs == 2
+            assert s.npairs == nunits and s.half_plane == half
             s.set_peers(slabs)
             s.set_psf_motion(9, 30.0, K)
         st = torch.cuda.Stream(device=dev)
-        sts = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        sts = [torch.cuda.Stream(device=dev) for _ in range(nunits)]
         rb = W * 3
         for ph in (1, 2, 3):
-            for pair in (1, 0):  # order between pairs must not matter; the two pairs run concurrently
+            for pair in reversed(range(nunits)):  # order between units must not matter; they run concurrently
                 for s in shards:
                     if ph == 1:
                         s.phase1(d_in.data_ptr() + s.first_row * rb, sts[pair].cuda_stream, pair=pair)
@@ -123,11 +197,12 @@ def test_sharded_4096_world8(gpu, oracle):
     torch = pytest.importorskip("torch")
     H = W = 4096
     img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(2, 0, H, W), (1, 2, 0)))
-    got, _ = run_emulated(gpu, torch, img, 8, 50, 30.0)
-    with gpu.Plan(H, W, 3) as p:
-        p.set_psf_motion(50, 30.0, K)
-        single = p.restore_images_u8(img[None])[0]
+    got, _ = run_emulated(gpu, torch, img, 8, 50, 30.0, half=False)
+    single = single_gpu(gpu, img, 50, 30.0, half=False)
     assert np.array_equal(got, single)
+    got_h, _ = run_emulated(gpu, torch, img, 8, 50, 30.0, half=True)
+    exact, off1, worse = u8_gate(got_h, single)
+    assert worse == 0 and off1 <= 1e-3 * got_h.size, (exact, off1, worse)
 
 
 def test_synth_rows_match_whole_image(gpu, oracle):
