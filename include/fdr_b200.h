@@ -206,8 +206,18 @@ int fdr_shard_set_row_ctas(fdr_shard* shard, int ctas);
 /* enabled: the vector of fdr_shard_minmax_device holds (min, -max) per plane so that ONE all-reduce(MIN) over all of it
  * folds both extrema; phase 4 undoes the sign.  Default off (column 0 MIN, column 1 MAX). */
 int fdr_shard_set_minmax_negated(fdr_shard* shard, int enabled);
+/* Cross-rank synchronisation through flags in peer memory (the slab allocation carries them, so fdr_shard_set_peers is all
+ * the set-up they need).  They replace the synchronisation implied by MPI_Alltoallv (fft_mpi.cpp:170-279) and keep NCCL /
+ * MPI out of the per-image path.  fdr_shard_barrier: stream-ordered barrier; every rank calls it with the same `set`
+ * (0..15; independent sequences, one per concurrently running pipeline unit and phase) in the same order.
+ * fdr_shard_minmax_allreduce: all-reduce of the extrema vector below in one launch (it is also a barrier).  A barrier gives
+ * up after 20 s if a peer never arrives; fdr_shard_sync_status synchronises `stream` and reports that.  Shards that share
+ * one device (tests) must issue these on one stream per shard, or the waits would queue behind each other. */
+int fdr_shard_barrier(fdr_shard* shard, int set, void* stream);
+int fdr_shard_minmax_allreduce(fdr_shard* shard, void* stream);
+int fdr_shard_sync_status(fdr_shard* shard, void* stream, int* timed_out);
 /* [channels][2] floats (min, max of this rank's part of every padded plane) to all-reduce in
- * place: column 0 with MIN, column 1 with MAX. */
+ * place: column 0 with MIN, column 1 with MAX (fdr_shard_minmax_allreduce does it over peer memory). */
 int fdr_shard_minmax_device(fdr_shard* shard, void** d_minmax_f32);
 int fdr_shard_phase4_pack(fdr_shard* shard, void* d_out_rows_u8, void* stream);
 int fdr_shard_last_launch_count(const fdr_shard* shard, long long* launches);

@@ -69,10 +69,91 @@ struct fdr_shard {
     std::vector<float2*> peer_host;  // host copy of the peer slab table
     int row_ctas = 0;           // > 0: exchange passes run as at most this many persistent CTAs per unit
     int minmax_neg = 0;         // mmf holds (min, -max): one all-reduce(MIN) folds both
+    // peer synchronisation area at the tail of the slab allocation (so the slab's IPC handle covers it): barrier flags
+    // [SYNC_SETS][FDR_MAX_PEERS] u32, then the extrema mailbox [2][FDR_MAX_PEERS][C][2] f32, then one status word
+    size_t sync_off = 0;        // element (float2) offset of the area inside the slab allocation
+    unsigned int epoch[16] = {};  // barriers issued so far per flag set (every rank issues the same sequence)
+    unsigned int mm_epoch = 0;
 };
 
 namespace {
 cudaStream_t pick(fdr_shard* s, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : s->stream; }
+
+// ---- cross-GPU synchronisation through peer memory (replaces MPI_Barrier / the implicit synchronisation of
+// MPI_Alltoallv, fft_mpi.cpp:170-279, and the MPI_Allreduce-style min/max of a distributed normalize) ----
+constexpr int SYNC_SETS = 16;
+constexpr unsigned long long SYNC_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;  // a dead peer must not hang the GPU
+struct SyncPeers {
+    unsigned int* area[FDR_MAX_PEERS];  // every rank's synchronisation area
+};
+size_t sync_area_elems(int channels) {  // in float2 units
+    const size_t bytes = sizeof(unsigned int) * SYNC_SETS * FDR_MAX_PEERS + sizeof(float) * 2 * FDR_MAX_PEERS * channels * 2 + 64;
+    return (bytes + 7) / 8;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// thread i: tell rank i that `rank` reached `epoch` of flag set `set`, then wait until rank i has told us the same
+__device__ __forceinline__ void peer_signal_wait(const SyncPeers& sp, int rank, int world, int set, unsigned int epoch, unsigned int* status) {
+    const int i = threadIdx.x;
+    if (i < world) {
+        __threadfence_system();  // everything this GPU wrote before (also by earlier kernels of the stream) precedes the flag
+        st_release_sys(sp.area[i] + set * FDR_MAX_PEERS + rank, epoch);
+        const unsigned int* mine = sp.area[rank] + set * FDR_MAX_PEERS + i;
+        const unsigned long long t0 = global_ns();
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (global_ns() - t0 > SYNC_TIMEOUT_NS) {
+                atomicExch(status, 1u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+__global__ void peer_barrier_kernel(SyncPeers sp, int rank, int world, int set, unsigned int epoch, unsigned int* status) {
+    peer_signal_wait(sp, rank, world, set, epoch, status);
+}
+// All-reduce of the [C][2] extrema over peer memory in one launch: every rank drops its vector into every rank's mailbox
+// (slot `epoch & 1`), barrier, fold.  negated: both columns fold with MIN (the vector holds (min, -max)).
+__global__ void peer_minmax_kernel(SyncPeers sp, int rank, int world, int set, unsigned int epoch, unsigned int* status, float* mmf,
+                                   int n, int negated) {
+    const size_t box_off = (size_t)SYNC_SETS * FDR_MAX_PEERS;  // in 4-byte words
+    const size_t slot = (size_t)(epoch & 1u) * FDR_MAX_PEERS * n;
+    for (int j = threadIdx.x; j < world * n; j += blockDim.x) {
+        const int dst = j / n, e = j - dst * n;
+        float* box = reinterpret_cast<float*>(sp.area[dst] + box_off) + slot + (size_t)rank * n;
+        box[e] = mmf[e];
+    }
+    __syncthreads();
+    peer_signal_wait(sp, rank, world, set, epoch, status);
+    const float* boxes = reinterpret_cast<const float*>(sp.area[rank] + box_off) + slot;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        float v = __ldcg(boxes + e);
+        for (int r = 1; r < world; ++r) {
+            const float w = __ldcg(boxes + (size_t)r * n + e);
+            v = ((e & 1) && !negated) ? fmaxf(v, w) : fminf(v, w);
+        }
+        mmf[e] = v;
+    }
+}
+SyncPeers sync_peers(const fdr_shard* s) {
+    SyncPeers sp{};
+    for (int i = 0; i < s->world; ++i) sp.area[i] = reinterpret_cast<unsigned int*>(s->peer_host[(size_t)i] + s->sync_off);
+    return sp;
+}
+unsigned int* sync_status(const fdr_shard* s) {
+    return reinterpret_cast<unsigned int*>(s->slab.p + s->sync_off) + SYNC_SETS * FDR_MAX_PEERS + 2 * FDR_MAX_PEERS * s->C * 2;
+}
 
 // half-plane forms: column owners' slabs and the Nyquist vectors (inside the same allocations) by value in the launch arguments
 void fill_half_peers(const fdr_shard* s, RowPassArgs& r) {
@@ -230,12 +311,27 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
     if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "shard setup: %s", cudaGetErrorString(e));
     if (s->half) {
         s->nyq_off = (size_t)channels * Rp * s->Ch;
-        if (rc == FDR_OK) rc = s->slab.ensure(s->nyq_off + (size_t)channels * Rp);
+        s->sync_off = (s->nyq_off + (size_t)channels * Rp + 31) & ~(size_t)31;
+        if (rc == FDR_OK) rc = s->slab.ensure(s->sync_off + sync_area_elems(channels));
         if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Ch);
         if (rc == FDR_OK) rc = s->wiener_nyq.ensure((size_t)Rp);
     } else {
-        if (rc == FDR_OK) rc = s->slab.ensure((size_t)s->npairs * Rp * s->Cl);
+        s->sync_off = ((size_t)s->npairs * Rp * s->Cl + 31) & ~(size_t)31;
+        if (rc == FDR_OK) rc = s->slab.ensure(s->sync_off + sync_area_elems(channels));
         if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Cl);
+    }
+    if (rc == FDR_OK && world > FDR_MAX_PEERS) rc = set_error(FDR_E_INVALID, "at most %d ranks", FDR_MAX_PEERS);
+    if (rc == FDR_OK) {
+        // Load the waiting kernels now: with lazy module loading the first launch of a kernel may block the host until the
+        // device is idle, which never happens while another shard of this process spins in a barrier.
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_barrier_kernel));
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_minmax_kernel));
+        if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "sync kernels: %s", cudaGetErrorString(e));
+    }
+    if (rc == FDR_OK) {  // flags and mailboxes start at zero (before any peer can have the handle)
+        e = cudaMemset(s->slab.p + s->sync_off, 0, sync_area_elems(channels) * sizeof(float2));
+        if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "sync area: %s", cudaGetErrorString(e));
     }
     if (rc == FDR_OK) rc = s->raw.ensure((size_t)channels * (s->rows_local > 0 ? s->rows_local : 1) * cols);
     if (rc == FDR_OK) rc = s->mm.ensure((size_t)channels * 2 * FDR_MINMAX_SLOTS);
@@ -545,6 +641,45 @@ FDR_API int fdr_shard_phase4_pack(fdr_shard* s, void* d_out_rows_u8, void* strea
     FDR_CUDA(launch_pack_u8(s->raw.p, (long long)s->rows_local * s->W, s->ss.p, static_cast<uint8_t*>(d_out_rows_u8), 1, s->C,
                             s->rows_local, s->W, st));
     s->launches += 1;
+    return FDR_OK;
+}
+
+// Cross-rank barrier on `stream` through flags in peer memory: every rank must call it with the same `set` in the same order.
+// Work queued on the stream after it starts only when every rank's work queued before its own call has completed and is
+// visible.  Different sets are independent sequences (one per concurrently running pipeline unit and phase).
+FDR_API int fdr_shard_barrier(fdr_shard* s, int set, void* stream) {
+    if (!s || set < 0 || set >= SYNC_SETS) return set_error(FDR_E_INVALID, "bad barrier arguments (sets 0..%d)", SYNC_SETS - 1);
+    if (!s->have_peers) return set_error(FDR_E_STATE, "barrier before fdr_shard_set_peers");
+    FDR_CUDA(cudaSetDevice(s->device));
+    const unsigned int ep = ++s->epoch[set];
+    peer_barrier_kernel<<<1, 32, 0, pick(s, stream)>>>(sync_peers(s), s->rank, s->world, set, ep, sync_status(s));
+    FDR_CUDA(cudaGetLastError());
+    s->launches += 1;
+    return FDR_OK;
+}
+
+// Global extrema of every padded plane: all-reduce of the [channels][2] vector of fdr_shard_minmax_device over peer
+// memory (one launch, also a barrier: afterwards every rank has finished phase 3, so the slabs are free for the next image).
+FDR_API int fdr_shard_minmax_allreduce(fdr_shard* s, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    if (!s->have_peers) return set_error(FDR_E_STATE, "all-reduce before fdr_shard_set_peers");
+    FDR_CUDA(cudaSetDevice(s->device));
+    const unsigned int ep = ++s->mm_epoch;
+    peer_minmax_kernel<<<1, 128, 0, pick(s, stream)>>>(sync_peers(s), s->rank, s->world, SYNC_SETS - 1, ep, sync_status(s), s->mmf.p,
+                                                        2 * s->C, s->minmax_neg);
+    FDR_CUDA(cudaGetLastError());
+    s->launches += 1;
+    return FDR_OK;
+}
+
+// 0 = every barrier so far completed; 1 = one gave up after its time-out (a peer never arrived).  Synchronises `stream`.
+FDR_API int fdr_shard_sync_status(fdr_shard* s, void* stream, int* timed_out) {
+    if (!s || !timed_out) return set_error(FDR_E_INVALID, "bad arguments");
+    FDR_CUDA(cudaSetDevice(s->device));
+    FDR_CUDA(cudaStreamSynchronize(pick(s, stream)));
+    unsigned int v = 0;
+    FDR_CUDA(cudaMemcpy(&v, sync_status(s), sizeof(v), cudaMemcpyDeviceToHost));
+    *timed_out = v != 0;
     return FDR_OK;
 }
 

@@ -100,6 +100,9 @@ def lib():
             "fdr_shard_half_plane": [vp, C.POINTER(i)],
             "fdr_shard_set_row_ctas": [vp, i],
             "fdr_shard_set_minmax_negated": [vp, i],
+            "fdr_shard_barrier": [vp, i, vp],
+            "fdr_shard_minmax_allreduce": [vp, vp],
+            "fdr_shard_sync_status": [vp, vp, C.POINTER(i)],
             "fdr_shard_minmax_device": [vp, pp],
             "fdr_shard_phase4_pack": [vp, vp, vp],
             "fdr_shard_last_launch_count": [vp, C.POINTER(ll)],
@@ -354,6 +357,17 @@ class Shard:
     def set_minmax_negated(self, on=True):
         _check(lib().fdr_shard_set_minmax_negated(self.h, int(on)))
         self.minmax_negated = bool(on)
+
+    def peer_barrier(self, set_index, stream=0):
+        _check(lib().fdr_shard_barrier(self.h, int(set_index), stream))
+
+    def minmax_allreduce(self, stream=0):
+        _check(lib().fdr_shard_minmax_allreduce(self.h, stream))
+
+    def sync_timed_out(self, stream=0):
+        v = C.c_int(0)
+        _check(lib().fdr_shard_sync_status(self.h, stream, C.byref(v)))
+        return bool(v.value)
 
     def phase1(self, d_in_rows, stream=0, pair=None):
         if pair is None:

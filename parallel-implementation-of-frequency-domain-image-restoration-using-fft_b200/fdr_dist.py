@@ -9,6 +9,8 @@ Two granularities:
     torch.distributed.  Replaces the reference's MPI driver loop (mpi.cpp:95-111 +
     fft_mpi.cpp:311-470).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -76,6 +78,9 @@ class ShardedRestorer:
         self._flag = torch.zeros(1, dtype=torch.float32, device=self._mm.device)
         self._side = None                             # side streams + flags of the unit pipeline
         self._cuda = self._mm.is_cuda
+        # per-image synchronisation over peer memory instead of NCCL collectives (FDR_SHARD_PEER_SYNC=0 selects NCCL)
+        self.peer_sync = (self._cuda and self.world > 1 and hasattr(backend, "peer_barrier")
+                          and os.environ.get("FDR_SHARD_PEER_SYNC", "1") != "0")
 
     def set_psf_motion(self, length, angle_deg, K):
         """PSF + Wiener factor on every rank, then a cross-rank fence: the build uses the rank's column slab as
@@ -93,14 +98,22 @@ class ShardedRestorer:
                 torch.cuda.synchronize()
             dist.barrier(group=self.group)
 
-    def barrier(self, flag=None):
-        """Stream-ordered cross-rank barrier: a 1-element all-reduce on the current stream."""
-        if self.world > 1:
+    def barrier(self, flag=None, set_index=0, stream=None):
+        """Stream-ordered cross-rank barrier: flags in peer memory (fdr_shard_barrier) when the backend has them and
+        `peer_sync` is on, else a 1-element all-reduce on the current stream through torch.distributed."""
+        if self.world <= 1:
+            return
+        if self.peer_sync:
+            self.b.peer_barrier(set_index, torch.cuda.current_stream(self._mm.device).cuda_stream if stream is None else stream)
+        else:
             dist.all_reduce(self._flag if flag is None else flag, group=self.group)
 
     def _reduce_minmax(self):
         """Global extrema of every padded plane (also the barrier that frees the slabs for the next image)."""
         if self.world <= 1:
+            return
+        if self.peer_sync:
+            self.b.minmax_allreduce(torch.cuda.current_stream(self._mm.device).cuda_stream)
             return
         if getattr(self.b, "minmax_negated", False):
             dist.all_reduce(self._mm, op=dist.ReduceOp.MIN, group=self.group)  # (min, -max): one collective
@@ -131,7 +144,7 @@ class ShardedRestorer:
                     else:
                         b.phase3(st.cuda_stream, pair=unit)
                     if phase < 3:
-                        self.barrier(flag)
+                        self.barrier(flag, set_index=2 * unit + phase - 1, stream=st.cuda_stream)
         for st, _ in self._side:
             main.wait_stream(st)
 
@@ -149,13 +162,13 @@ class ShardedRestorer:
                                  "set_stream); the cross-rank barriers are ordered against that stream only")
         elif stream is None:
             stream = 0
-        if (pipeline_pairs and self._cuda and self.world > 1 and getattr(b, "supports_pair_pipeline", False) and b.npairs >= 2):
+        if (pipeline_pairs and self._cuda and self.world > 1 and getattr(b, "supports_pair_pipeline", False) and 2 <= b.npairs <= 6):   # flag sets 0..11 belong to the units
             self._restore_rows_unit_pipeline(d_in_rows, cur)
         else:
             b.phase1(d_in_rows, stream)
-            self.barrier()                      # every slab has received all its columns
+            self.barrier(set_index=13, stream=stream)   # every slab has received all its columns
             b.phase2(stream)
-            self.barrier()                      # every slab holds the filtered, column-inverted data
+            self.barrier(set_index=14, stream=stream)   # every slab holds the filtered, column-inverted data
             b.phase3(stream)
         self._reduce_minmax()
         b.phase4(d_out_rows, stream)

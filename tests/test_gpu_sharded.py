@@ -213,3 +213,41 @@ def test_synth_rows_match_whole_image(gpu, oracle):
     gpu.synth_rows_device_u8(d.data_ptr(), 0xF17E0000 + 4, 3, 3, H, W, 17, 40, 0)
     torch.cuda.synchronize()
     assert np.array_equal(d.cpu().numpy(), whole[17:57])
+
+
+@pytest.mark.parametrize("world,negated", [(2, True), (4, False), (8, True)])
+def test_peer_barrier_and_minmax_allreduce(gpu, oracle, world, negated):
+    """fdr_shard_barrier / fdr_shard_minmax_allreduce: flags and mailboxes in peer memory.  The shards share one device
+    here, so each gets its own stream (the waits must be co-resident); three rounds to exercise the epochs and the
+    double-buffered mailbox."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda", 0)
+    dist_mod = _load("fdr_dist", PKG + "/fdr_dist.py")
+    H, W, C = 64, 128, 3
+    shards = [gpu.Shard(H, W, C, g, world, 0) for g in range(world)]
+    try:
+        slabs = [s.local_slab()[0] for s in shards]
+        for s in shards:
+            s.set_peers(slabs)
+            s.set_minmax_negated(negated)
+        sts = [torch.cuda.Stream(device=dev) for _ in range(world)]
+        mms = [dist_mod.device_tensor(s.minmax_ptr(), (C, 2), dev) for s in shards]
+        rng = np.random.default_rng(world)
+        for rnd in range(3):
+            vals = rng.standard_normal((world, C, 2)).astype(np.float32)
+            for g, t in enumerate(mms):
+                t.copy_(torch.from_numpy(vals[g]))
+            torch.cuda.synchronize()
+            for g, s in enumerate(shards):
+                s.peer_barrier(rnd % 3, sts[g].cuda_stream)
+                s.minmax_allreduce(sts[g].cuda_stream)
+            for g, s in enumerate(shards):
+                assert not s.sync_timed_out(sts[g].cuda_stream)
+            want = vals.min(0)
+            if not negated:
+                want[:, 1] = vals[:, :, 1].max(0)
+            for t in mms:
+                assert np.array_equal(t.cpu().numpy(), want)
+    finally:
+        for s in shards:
+            s.close()
