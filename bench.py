@@ -176,14 +176,53 @@ def run_reference(args):
     return 0
 
 
-def run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H, W, plen, pang, seed):
-    """One image row-sharded over `world` GPUs (BASELINE configs[4]); strong scaling.  Exchanges are
-    peer stores/loads fused into the row passes; NCCL carries only barriers and the min/max."""
+def pcie_roofline(torch, dist, dev, world, mb=256, reps=4):
+    """Measured concurrent pinned H2D + D2H rate of this rank's GPU while every rank does the same (the end-to-end bound)."""
+    n = mb << 20
+    hin = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    a = torch.empty(n, dtype=torch.uint8, device=dev)
+    b = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    for _ in range(1):
+        with torch.cuda.stream(s1):
+            a.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(b, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        with torch.cuda.stream(s1):
+            a.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(b, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    each = n * reps / dt / 1e9
+    del hin, hout, a, b
+    return {"GBps_each_way_per_gpu": each, "GBps_each_way_all_gpus": each * world,
+            "how": "%d MiB pinned H2D and D2H concurrently on two streams, x%d, all %d ranks at once, slowest rank" % (mb, reps, world)}
+
+
+def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H, W, plen, pang, seed, steps, warmup,
+                    want_e2e=True, parity_mode="oracle"):
+    """One image row-sharded over `world` GPUs (BASELINE configs[4]); strong scaling.  The transposes of the reference's
+    MPI_Alltoallv (fft_mpi.cpp:170-279, 284-307) are peer stores/loads fused into the row passes; barriers and the min/max
+    all-reduce run over flags in peer memory; torch.distributed (NCCL) only exchanges the IPC handles and fences the PSF
+    build.  Collective: every rank calls it; returns the result dict on every rank (parity only on rank 0)."""
     import numpy as np
     fd = _load("fdr_dist", os.path.join(PKG, "fdr_dist.py"))
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
+    stream = torch.cuda.current_stream(dev)
     sh = stream.cuda_stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # nvidia-smi needs ~1 s to start: begin before set-up and warm-up so the timed region is covered
     back = fd.cuda_shard_backend(fdr, H, W, 3, rank, world, local_rank)
     drv = fd.ShardedRestorer(back, device=dev)
     drv.set_psf_motion(plen, pang, K_WIENER)  # builds the Wiener slab on every rank, then fences across ranks
@@ -191,147 +230,302 @@ def run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H
     d_in = torch.empty((max(n_rows, 1), W, 3), dtype=torch.uint8, device=dev)
     d_out = torch.empty_like(d_in)
     fdr.synth_rows_device_u8(d_in.data_ptr(), seed, 0, 3, H, W, first, n_rows, sh)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
     torch.cuda.synchronize()
 
     def step():
-        if flush is not None:
-            fdr.l2_flush(flush.data_ptr(), flush.numel(), sh)
         drv.restore_rows(d_in.data_ptr(), d_out.data_ptr(), sh)
 
-    for _ in range(args.warmup):
+    t_w0 = time.perf_counter()
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
+    while time.perf_counter() - t_w0 < 1.5:   # keep the GPUs busy until the clock sampler has started reporting
+        step()
+        torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
+    torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-
-    # per-phase device times (separate short pass so the events do not perturb the timed region)
-    ph = [0.0, 0.0, 0.0, 0.0]
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    reps = max(1, min(args.steps, 3))
-    for _ in range(reps):
-        b = back
-        evs[0].record(stream)
-        b.phase1(d_in.data_ptr(), sh)
-        evs[1].record(stream)
-        drv.barrier()
-        e_a = torch.cuda.Event(enable_timing=True)
-        e_a.record(stream)
-        b.phase2(sh)
-        evs[2].record(stream)
-        drv.barrier()
-        e_b = torch.cuda.Event(enable_timing=True)
-        e_b.record(stream)
-        b.phase3(sh)
-        evs[3].record(stream)
-        mn = drv._mm[:, 0].contiguous()
-        mx = drv._mm[:, 1].contiguous()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        drv._mm[:, 0].copy_(mn)
-        drv._mm[:, 1].copy_(mx)
-        e_c = torch.cuda.Event(enable_timing=True)
-        e_c.record(stream)
-        b.phase4(d_out.data_ptr(), sh)
-        evs[4].record(stream)
+    ms_step = float(t.item()) / steps
+    # a longer busy stretch of the same step so that the 200 ms sampler sees the clocks under this load
+    t_b0 = time.perf_counter()
+    while time.perf_counter() - t_b0 < 1.0:
+        for _ in range(20):
+            step()
         torch.cuda.synchronize()
-        ph[0] += evs[0].elapsed_time(evs[1])
-        ph[1] += e_a.elapsed_time(evs[2])
-        ph[2] += e_b.elapsed_time(evs[3])
-        ph[3] += e_c.elapsed_time(evs[4])
-    ph = [x / reps for x in ph]
-    pt = torch.tensor(ph, dtype=torch.float64, device=dev)
+    clocks = sampler.stop()
+    dist.barrier()
+
+    # per-phase device times of the serial schedule (separate pass; the timed region above runs the pipelined driver)
+    ph = np.zeros(5)
+    reps = 3
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+        ev[0].record(stream)
+        back.phase1(d_in.data_ptr(), sh)
+        ev[1].record(stream)
+        drv.barrier(set_index=13, stream=sh)
+        ev[2].record(stream)
+        back.phase2(sh)
+        ev[3].record(stream)
+        drv.barrier(set_index=14, stream=sh)
+        ev[4].record(stream)
+        back.phase3(sh)
+        ev[5].record(stream)
+        drv._reduce_minmax()
+        ev[6].record(stream)
+        back.phase4(d_out.data_ptr(), sh)
+        ev[7].record(stream)
+        torch.cuda.synchronize()
+        ph += np.array([ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3]), ev[4].elapsed_time(ev[5]), ev[6].elapsed_time(ev[7]),
+                        ev[0].elapsed_time(ev[7])])
+    pt = torch.tensor(ph / reps, dtype=torch.float64, device=dev)
     dist.all_reduce(pt, op=dist.ReduceOp.MAX)
     ph = [float(x) for x in pt.tolist()]
 
-    # end to end: pinned host rows -> device -> restore -> pinned host rows, every step
+    # end to end: pinned host rows -> device -> restore -> pinned host rows every step, double-buffered so that the copies of
+    # neighbouring steps overlap the restore (three streams)
     e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         hin = torch.empty(d_in.shape, dtype=torch.uint8, pin_memory=True)
-        hout = torch.empty(d_in.shape, dtype=torch.uint8, pin_memory=True)
+        hout = [torch.empty(d_in.shape, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
         hin.copy_(d_in)
-        torch.cuda.synchronize()
+        dins = [d_in, torch.empty_like(d_in)]
+        douts = [d_out, torch.empty_like(d_out)]
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        n_e = max(4, args.e2e_steps * 4)
+
+        def e2e_loop(n):
+            for i in range(n):
+                b = i & 1
+                with torch.cuda.stream(s_in):
+                    if i >= 2:
+                        s_in.wait_event(ev_cmp[b])       # the restore that read dins[b] two steps ago
+                    dins[b].copy_(hin, non_blocking=True)
+                    ev_in[b].record(s_in)
+                stream.wait_event(ev_in[b])
+                if i >= 2:
+                    stream.wait_event(ev_out[b])         # douts[b] has been copied out
+                drv.restore_rows(dins[b].data_ptr(), douts[b].data_ptr(), sh)
+                ev_cmp[b].record(stream)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[b])
+                    hout[b].copy_(douts[b], non_blocking=True)
+                    ev_out[b].record(s_out)
+            torch.cuda.synchronize()
+
+        e2e_loop(2)
         dist.barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            d_in.copy_(hin, non_blocking=True)
-            drv.restore_rows(d_in.data_ptr(), d_out.data_ptr(), sh)
-            hout.copy_(d_out, non_blocking=True)
-            stream.synchronize()
+        e2e_loop(n_e)
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": H * W * args.e2e_steps / float(tt.item()) / 1e6, "unit": "Mpixel/s",
-               "h2d_bytes_per_step": int(hin.numel()) * world, "d2h_bytes_per_step": int(hout.numel()) * world,
-               "steps": args.e2e_steps, "ms_per_step": float(tt.item()) / args.e2e_steps * 1e3}
+        e2e = {"value": H * W * n_e / float(tt.item()) / 1e6, "unit": "Mpixel/s",
+               "h2d_bytes_per_step": int(hin.numel()) * world, "d2h_bytes_per_step": int(hout[0].numel()) * world,
+               "steps": n_e, "ms_per_step": float(tt.item()) / n_e * 1e3,
+               "api": "ShardedRestorer.restore_rows on pinned host row slabs, H2D / restore / D2H of neighbouring steps overlapped (double-buffered)"}
+        e2e["matches_device"] = bool(torch.equal(hout[(n_e - 1) & 1][:n_rows], d_out[:n_rows].cpu()) if n_rows else True)
+        del hin, hout, dins, douts
 
-    # parity gate (iii): the sharded rows of rank 0 against the single-GPU path of the same library
+    # parity: plane 0 (B) of the WHOLE image against the reference's CPU code at full size (oracle/_ref openmp mode, which
+    # agrees with its serial mode to 1e-7; the serial port otherwise), fft_serial.cpp:141-261
+    step()
+    torch.cuda.synchronize()
     parity = None
-    if rank == 0 and not args.no_check:
-        whole = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
-        ref_out = torch.empty_like(whole)
-        fdr.synth_images_device_u8(whole.data_ptr(), seed, 0, 1, 3, H, W, sh)
-        with fdr.Plan(H, W, 3, 1, local_rank) as plan:
-            plan.set_psf_motion(plen, pang, K_WIENER)
-            plan.restore_images_device_u8(whole.data_ptr(), ref_out.data_ptr(), 1, sh)
-            torch.cuda.synchronize()
-        a = d_out[:n_rows].cpu().numpy().astype(np.int16)
-        b = ref_out[first:first + n_rows].cpu().numpy().astype(np.int16)
-        d = np.abs(a - b)
-        parity = {"against": "single-GPU path of this library, rows of rank 0", "pixels": int(d.size), "exact": int((d == 0).sum()),
-                  "off_by_1": int((d == 1).sum()), "off_by_more": int((d > 1).sum())}
-        del whole, ref_out
+    if parity_mode != "none":
+        mine = d_out[:, :, 0].contiguous() if parity_mode == "oracle" else d_out.contiguous()
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if rank == 0:
+            got = torch.cat(parts)[:H].cpu().numpy()
+            if parity_mode == "oracle":
+                O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+                psf = O.port().motion_psf(plen, pang)
+                img0 = O.synth_image_u8(cfg_idx, 0, H, W)[0]
+                pl = O.pad_pow2(img0.astype(np.float32) * np.float32(1.0 / 255.0))
+                t0 = time.perf_counter()
+                if O.have_ref():
+                    O.ref().set_threads(os.cpu_count() or 1)
+                    norm = O.ref().wiener(pl, psf, K_WIENER, "openmp")[:H, :W]
+                    how = "reference fft_openmp.cpp compiled unmodified (oracle/_ref), %d threads" % (os.cpu_count() or 1)
+                else:
+                    norm = O.port().wiener_deblur(pl, psf, K_WIENER)["norm"][:H, :W]
+                    how = "oracle port (serial)"
+                t_cpu = time.perf_counter() - t0
+                want = O.port().pack_u8(norm)
+                against = "%s on the whole %dx%d plane 0, %.1f s" % (how, H, W, t_cpu)
+            else:
+                whole = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+                ref_out = torch.empty_like(whole)
+                fdr.synth_images_device_u8(whole.data_ptr(), seed, 0, 1, 3, H, W, sh)
+                with fdr.Plan(H, W, 3, 1, local_rank) as plan:
+                    plan.set_psf_motion(plen, pang, K_WIENER)
+                    plan.restore_images_device_u8(whole.data_ptr(), ref_out.data_ptr(), 1, sh)
+                    torch.cuda.synchronize()
+                want = ref_out.cpu().numpy()
+                against = "single-GPU path of this library, whole image"
+                del whole, ref_out
+            d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+            parity = {"against": against, "pixels": int(d.size), "exact": int((d == 0).sum()), "off_by_1": int((d == 1).sum()),
+                      "off_by_more": int((d > 1).sum()), "frac_within_1": float((d <= 1).mean())}
+        dist.barrier()
+    timed_out = back.sync_timed_out(sh)
     launches = back.last_launch_count()
+    half = back.half_plane
+    Rp, Cp = back.padded_rows, back.padded_cols
+    back.close()
+    peak, peak_src = measured_peak_gbs()
+    planes_c = 1.5 if half else 2.0                                   # complex planes through the exchange and the column phase
+    col_bytes_px = 56.0 if Rp >= 8192 else 24.0                       # K x 2048 block scheme: three sweeps
+    bytes_p2 = col_bytes_px * Rp * (Cp / world) * planes_c            # per rank
+    nvlink_bytes_phase = 8.0 * Rp * Cp / world * (world - 1) / world * planes_c   # per rank, per exchange
+    names = ["phase1_rows_fwd_scatter", "phase2_cols_wiener", "phase3_gather_rows_inv", "phase4_pack"]
+    chan_px = H * W * 3
+    res = {
+        "workload": "rgb16384" if H == 16384 else "%dx%dx3" % (H, W), "image": [H, W, 3], "n_gpus": world,
+        "ms_per_step": ms_step, "value": H * W / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s", "steps": steps, "warmup": warmup,
+        "scaling": "strong", "half_plane": bool(half), "peer_sync": bool(drv.peer_sync), "unit_pipeline": True,
+        "phases_ms_serial_schedule": dict(zip(names + ["total"], ph)),
+        "phase2_hbm": {"bytes_per_gpu": bytes_p2, "GBps": bytes_p2 / (ph[1] * 1e-3) / 1e9 if ph[1] > 0 else None,
+                       "frac_of_peak": bytes_p2 / (ph[1] * 1e-3) / 1e9 / peak if ph[1] > 0 else None, "peak": peak, "peak_source": peak_src},
+        "nvlink": {"bytes_per_gpu_per_exchange": nvlink_bytes_phase, "measured_peer_GBps": 770.0,
+                   "bound_ms_both_exchanges": 2 * nvlink_bytes_phase / 770e9 * 1e3,
+                   "phase1_GBps": nvlink_bytes_phase / (ph[0] * 1e-3) / 1e9 if ph[0] > 0 else None,
+                   "phase3_GBps": nvlink_bytes_phase / (ph[2] * 1e-3) / 1e9 if ph[2] > 0 else None},
+        "contract53": {"bytes_per_channel_pixel": CONTRACT_BYTES_PER_CHANNEL_PIXEL,
+                       "GBps_aggregate": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (ms_step * 1e-3) / 1e9,
+                       "frac_of_aggregate_peak_contract53": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (ms_step * 1e-3) / 1e9 / (peak * world),
+                       "target_frac": 0.60, "target_ms": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (0.60 * peak * world * 1e9) * 1e3},
+        "e2e": e2e, "gpu_launches_per_step": int(launches), "clocks": clocks, "parity": parity, "barrier_timed_out": bool(timed_out),
+    }
+    return res
+
+
+def run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H, W, plen, pang, seed):
+    """--workload rgb16384 (or any single-image workload) at N > 1: the sharded measurement as the line itself."""
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    r = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H, W, plen, pang, seed, args.steps, args.warmup,
+                        want_e2e=not args.no_e2e, parity_mode="none" if args.no_check else args.sharded_parity)
     if rank != 0:
         dist.destroy_process_group()
         return 0
-    peak, peak_src = measured_peak_gbs()
-    Rp, Cp = back.padded_rows, back.padded_cols
-    npairs = 2
-    bytes_p2 = (8.0 * H * (Cp // world) + 16.0 * Rp * (Cp // world)) * npairs   # per rank
-    nvlink_bytes_per_gpu = 2 * 8.0 * Rp * Cp / world * (world - 1) / world * npairs  # out (phase 1) + in (phase 3)
-    dom = int(np.argmax(ph))
-    names = ["phase1_rows_fwd_scatter", "phase2_cols_wiener", "phase3_gather_rows_inv", "phase4_pack"]
-    chan_px = H * W * 3
-    value = H * W * args.steps / (ms_max * 1e-3) / 1e6
-    roofline = {
-        "bound": "hbm", "kernel": names[1], "achieved": bytes_p2 / (ph[1] * 1e-3) / 1e9 if ph[1] > 0 else 0.0, "peak": peak,
-        "unit": "GB/s", "frac": (bytes_p2 / (ph[1] * 1e-3) / 1e9 / peak) if ph[1] > 0 else 0.0, "traffic": None,
-        "peak_source": peak_src + " (of measured), per GPU", "phases_ms": dict(zip(names, ph)), "slowest_phase": names[dom],
-        "nvlink": {"bytes_per_gpu_per_image": nvlink_bytes_per_gpu, "measured_peer_GBps": 770.0,
-                   "bound_ms": nvlink_bytes_per_gpu / 770e9 * 1e3,
-                   "achieved_GBps_phase1_plus_3": nvlink_bytes_per_gpu / ((ph[0] + ph[2]) * 1e-3) / 1e9 if ph[0] + ph[2] > 0 else 0.0},
-        "pipeline": {"contract_bytes_per_channel_pixel": CONTRACT_BYTES_PER_CHANNEL_PIXEL,
-                     "GBps_contract53_aggregate": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px * args.steps / (ms_max * 1e-3) / 1e9,
-                     "frac_of_aggregate_peak_contract53": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px * args.steps / (ms_max * 1e-3) / 1e9 / (peak * world)},
-    }
     line = {
         "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
-        "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "value": r["value"], "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "image": [H, W, 3], "psf": [plen, pang], "K": K_WIENER,
-                   "parallelism": "row-sharded over %d GPUs, transposes fused as NVLink peer stores/loads, NCCL for barriers + min/max" % world,
-                   "l2": "flush between steps" if flush is not None else "working set larger than L2"},
-        "e2e": e2e, "gpu_launches": int(launches * args.steps), "clocks": clocks, "roofline": roofline,
-        "cpu_baseline": None, "parity": parity,
+                   "parallelism": "row-sharded over %d GPUs, transposes fused as NVLink peer stores/loads, barriers + min/max over "
+                                  "peer-memory flags" % world,
+                   "l2": "working set larger than L2"},
+        "e2e": r["e2e"], "gpu_launches": int(r["gpu_launches_per_step"] * args.steps), "clocks": r["clocks"],
+        "roofline": {"bound": "hbm", "kernel": "phase2_cols_wiener", "achieved": r["phase2_hbm"]["GBps"], "peak": r["phase2_hbm"]["peak"],
+                     "unit": "GB/s", "frac": r["phase2_hbm"]["frac_of_peak"], "traffic": None,
+                     "peak_source": r["phase2_hbm"]["peak_source"] + " (of measured), per GPU",
+                     "phases_ms": r["phases_ms_serial_schedule"], "nvlink": r["nvlink"], "pipeline": r["contract53"]},
+        "cpu_baseline": None, "parity": r["parity"], "sharded": r,
     }
     print(json.dumps(line))
     dist.destroy_process_group()
     return 0
+
+
+def side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, our_value):
+    """Same B200, same run: (1) the reference's own gpu mode (fft/fft_gpu.cu compiled unmodified for sm_100a,
+    oracle/_ref/libref_gpu.so) through its 3-plane host boundary as gpu.cpp:96-105 times it, beside this library through the
+    same boundary; (2) an eager torch.fft (cuFFT) pipeline with the same two-planes-per-transform packing, device resident.
+    Side comparisons only: neither is on the product path."""
+    import ctypes as C
+    import numpy as np
+    out = {}
+    O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+    psf = O.port().motion_psf(plen, pang)
+    lp = os.path.join(ROOT, "oracle", "_ref", "libref_gpu.so")
+    try:
+        if os.path.exists(lp):
+            lib = C.CDLL(lp)
+            fpp = C.POINTER(C.c_float)
+            lib.ref_gpu_restore.restype = C.c_double
+            lib.ref_gpu_restore.argtypes = [C.c_int, fpp, C.c_int, C.c_int, C.c_int, fpp, C.c_int, C.c_int, C.c_float]
+            planes = np.stack([O.synth_image_u8(3, 0, H, W)[c].astype(np.float32) / np.float32(255) for c in range(3)])
+            S = psf.shape[0]
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            saved = os.dup(1)
+            sys.stdout.flush()
+            os.dup2(devnull, 1)  # the reference prints its profile block on every call
+            try:
+                buf = planes.copy()
+                lib.ref_gpu_restore(0, buf.ctypes.data_as(fpp), 3, H, W, psf.ctypes.data_as(fpp), S, S, K_WIENER)
+                ts = []
+                for _ in range(3):
+                    buf = planes.copy()
+                    ts.append(lib.ref_gpu_restore(0, buf.ctypes.data_as(fpp), 3, H, W, psf.ctypes.data_as(fpp), S, S, K_WIENER))
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(devnull)
+            with fdr.Plan(H, W, 1) as p1:
+                p1.set_psf(psf, K_WIENER)
+                p1.restore_planes(list(planes))
+                to = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    p1.restore_planes(list(planes))
+                    to.append((time.perf_counter() - t0) * 1e3)
+            out["reference_gpu_mode"] = {"ms_per_image": min(ts), "Mpixel/s": H * W / (min(ts) * 1e-3) / 1e6,
+                                         "this_library_same_boundary_ms": min(to), "speedup": min(ts) / min(to),
+                                         "what": "fft_gpu::wienerDeblur_RGB_optimized of the reference (fft_gpu.cu:279-394, unmodified, sm_100a) "
+                                                 "on one %dx%dx3 image, 3 f32 host planes in and out, wall clock as gpu.cpp:96-105" % (H, W)}
+    except Exception as e:
+        out["reference_gpu_mode"] = {"unavailable": str(e)[:200]}
+    try:
+        Bc = min(64, d_in.shape[0])
+        dev = d_in.device
+        wf = torch.from_numpy(plan.get_wiener()).to(dev)
+
+        def cufft_pipeline(chunk=8):
+            for b0 in range(0, Bc, chunk):
+                x = d_in[b0:b0 + chunk].permute(0, 3, 1, 2).to(torch.float32) * (1.0 / 255.0)
+                zs = torch.cat([torch.complex(x[:, 0:1], x[:, 1:2]), torch.complex(x[:, 2:3], torch.zeros_like(x[:, 2:3]))], 1)
+                f = torch.fft.ifft2(torch.fft.fft2(zs) * wf, norm="forward")
+                pl = torch.cat([f[:, :1].real, f[:, :1].imag, f[:, 1:2].real], 1)
+                mn = pl.amin(dim=(2, 3), keepdim=True)
+                mx = pl.amax(dim=(2, 3), keepdim=True)
+                n = (pl - mn) / (mx - mn)
+                d_out[b0:b0 + chunk] = torch.clamp(torch.round(n * 255.0), 0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+
+        for _ in range(2):
+            cufft_pipeline()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            cufft_pipeline()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        cu = e0.elapsed_time(e1) / 3
+        mpx = Bc * H * W / (cu * 1e-3) / 1e6
+        out["cufft_torch_fft"] = {"Mpixel/s": mpx, "ms_per_%d_images" % Bc: cu, "this_library_Mpixel/s": our_value,
+                                  "speedup": our_value / mpx,
+                                  "what": "eager torch.fft.fft2 / ifft2 (cuFFT) + torch elementwise ops, device resident, same packing of two "
+                                          "planes per complex transform, %d images of %dx%dx3" % (Bc, H, W)}
+        del wf
+    except Exception as e:
+        out["cufft_torch_fft"] = {"unavailable": str(e)[:200]}
+    return out
 
 
 def main():
@@ -354,6 +548,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--flush-l2", action="store_true", help="overwrite a 512 MB scratch between steps (small workloads)")
     ap.add_argument("--replicas", action="store_true", help="single-image workloads at N>1: independent replicas instead of row sharding")
+    ap.add_argument("--sharded-parity", default="oracle", choices=["oracle", "self", "none"],
+                    help="row-sharded leg: check plane 0 of the whole image against the reference CPU code (default), the whole image "
+                         "against this library's single-GPU path, or nothing")
+    ap.add_argument("--no-sharded", action="store_true", help="N>1, batch workload: skip the row-sharded 16384^2 leg (BASELINE configs[4])")
+    ap.add_argument("--sharded-steps", type=int, default=20)
+    ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1)
@@ -476,6 +676,30 @@ def main():
         e2e_first = hout.array[0].copy()
         hin.free()
         hout.free()
+        pc = pcie_roofline(torch, dist, dev, world)
+        bound_ms = max(e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"]) / world / (pc["GBps_each_way_per_gpu"] * 1e9) * 1e3
+        e2e["roofline"] = {"bound": "pcie", "measured": pc, "bound_ms_per_step": bound_ms, "frac": bound_ms / e2e["ms_per_step"],
+                           "note": "end to end is bound by the host link: pinned H2D and D2H run concurrently with the kernels; with N ranks "
+                                   "on one host the copies share the host's memory and PCIe root complexes, so the per-GPU rate drops as N grows"}
+
+    padded = plan.padded
+    check_idx = sorted({0, max(0, B // 2 - 1), B - 1})   # first, middle, last image of the batch
+    got = {i: d_out[i].cpu().numpy() for i in check_idx} if rank == 0 else {}
+    got0 = got.get(0)
+    side = None
+    if rank == 0 and world == 1 and not args.no_side:
+        side = side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, value)
+    # ---- BASELINE configs[4] inside the same line when N > 1: one 16384^2 RGB image row-sharded over all ranks ----
+    sharded = None
+    if world > 1 and not args.no_sharded and args.workload == "batch256x2048":
+        del d_in, d_out
+        plan.close()
+        plan = None
+        torch.cuda.empty_cache()
+        c4, _, H4, W4, pl4, pa4 = WORKLOADS["rgb16384"]
+        sharded = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, c4, H4, W4, pl4, pa4, 0xF17E0000 + c4,
+                                  args.sharded_steps, max(3, args.warmup), want_e2e=not args.no_e2e,
+                                  parity_mode="none" if args.no_check else args.sharded_parity)
 
     if rank != 0:
         if world > 1:
@@ -498,21 +722,29 @@ def main():
     ksum = sum(v["ms"] for v in ktimes.values())
     form_bytes = sum(v["bytes"] for v in ktimes.values())
     chan_px = B * H * W * 3 * args.steps
-    Rp, Cp = plan.padded
+    Rp, Cp = padded
     iso_bytes = {"pass1_rows_fwd": (2.0 * H * W + 8.0 * H * Cp) * iso_pairs,
                  "pass2_cols_wiener": (8.0 * H * Cp + 16.0 * Rp * Cp) * iso_pairs,
                  "pass3_rows_inv_minmax": (8.0 * Rp * Cp + 8.0 * H * W) * iso_pairs}
     iso_ms = {"pass1_rows_fwd": isolated["pass1_ms"], "pass2_cols_wiener": isolated["pass2_ms"],
               "pass3_rows_inv_minmax": isolated["pass3_ms"]}
     rk = dom if dom in iso_ms else "pass2_cols_wiener"
-    achieved = iso_bytes[rk] / (iso_ms[rk] * 1e-3) / 1e9
+    iso_achieved = iso_bytes[rk] / (iso_ms[rk] * 1e-3) / 1e9
+    n_dom = max(1, ktimes[rk]["launches"])
     roofline = {
-        "bound": "hbm", "kernel": rk, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src + " (of measured, burst copy figure)",
-        "timing": "kernel launched alone on %d plane pairs (the chunk size of the step), mean of 10 launches, CUDA events on the "
-                  "launching stream inside bench.py right after the timed region; bytes = this formulation's algorithmic bytes" % iso_pairs,
-        "bytes_per_launch": iso_bytes[rk], "ms_per_launch": iso_ms[rk],
-        "isolated_GBps": {k: iso_bytes[k] / (iso_ms[k] * 1e-3) / 1e9 for k in iso_ms},
+        "bound": "hbm", "kernel": rk, "achieved": in_step_GBps if rk == dom else iso_achieved, "peak": peak, "unit": "GB/s",
+        "frac": (in_step_GBps if rk == dom else iso_achieved) / peak,
+        "traffic": traffic,
+        "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture of this kernel "
+                          "(profiles/traffic.json, per plane pair) scaled to the pairs of one launch; not re-measured in this run",
+        "peak_source": peak_src + " (of measured, copy figure)",
+        "timing": "algorithmic bytes of one launch / mean CUDA-event duration of this kernel's %d launches INSIDE the timed region "
+                  "(events on the launching stream, recorded by the library around every launch)" % n_dom,
+        "bytes_per_launch": ktimes[rk]["bytes"] / n_dom, "ms_per_launch": ktimes[rk]["ms"] / n_dom,
+        "isolated": {"note": "the same kernels launched alone on %d plane pairs (the chunk size of the step), mean of 10 launches, right "
+                             "after the timed region (secondary: the L2 is warmer and nothing else is in flight)" % iso_pairs,
+                     "frac": iso_achieved / peak, "ms_per_launch": iso_ms[rk],
+                     "GBps": {k: iso_bytes[k] / (iso_ms[k] * 1e-3) / 1e9 for k in iso_ms}},
         "in_step": {
             "note": "per-launch CUDA-event durations inside the timed region; chunks run on %s concurrent streams, so a launch's "
                     "duration includes time shared with other chunks' kernels" % os.environ.get("FDR_LANES", "1"),
@@ -542,7 +774,6 @@ def main():
         n_s = max(1, min(B, args.cpu_sample_images)) if want_cpu else 1
         mode = "serial"
         t_cpu = 0.0
-        got0 = d_out[0].cpu().numpy()
         worst = [0, 0, 0]
         for i in range(n_s):
             img = O.synth_image_u8(cfg_idx, first_image + i, H, W)
@@ -565,6 +796,34 @@ def main():
                             "kind": "reference" if O.have_ref() else "port",
                             "sample": "%d image(s) of %dx%dx3, reference serial mode (fft_serial.cpp compiled unmodified), %d host cores present"
                                       % (n_s, H, W, os.cpu_count() or 0)}
+        if parity is not None and O.have_ref() and len(check_idx) > 1:
+            # the other two images of SURVEY 8d(iv), against the reference's openmp mode (agrees with serial to ~1e-7)
+            O.ref().set_threads(os.cpu_count() or 1)
+            parity["more_images"] = []
+            for i in check_idx[1:]:
+                img = O.synth_image_u8(cfg_idx, first_image + i, H, W)
+                outs = [O.ref().wiener(O.pad_pow2(img[c].astype(np.float32) * np.float32(1.0 / 255.0)), psf, K_WIENER, "openmp")[:H, :W]
+                        for c in range(3)]
+                want = np.stack([O.port().pack_u8(o) for o in outs], -1)
+                d = np.abs(got[i].astype(np.int16) - want.astype(np.int16))
+                parity["more_images"].append({"image": first_image + i, "exact": int((d == 0).sum()), "off_by_1": int((d == 1).sum()),
+                                              "off_by_more": int((d > 1).sum()), "frac_within_1": float((d <= 1).mean())})
+    cpu_baselines = None
+    if want_cpu and O.have_ref() and not args.no_side:
+        # north_star: serial, OpenMP (and the SIMD and MPI modes) timed in the same run, one image each, on this host
+        cpu_baselines = {"serial": {"Mpixel/s": cpu_baseline["value"], "cores": 1}}
+        threads = os.cpu_count() or 1
+        for mode in ("simd", "openmp"):
+            tt = cpu_restore_images(O, mode, cfg_idx, 0, 1, H, W, psf, threads)
+            cpu_baselines[mode] = {"Mpixel/s": H * W / tt / 1e6, "cores": threads if mode == "openmp" else 1}
+        if O.have_ref_mpi():
+            ranks = max(1, min(threads, 16))
+            img = O.synth_image_u8(cfg_idx, 0, H, W)
+            pls = np.stack([O.pad_pow2(img[c].astype(np.float32) * np.float32(1.0 / 255.0)) for c in range(3)])
+            ms_mpi = O.ref_mpi_wiener(pls, psf, K_WIENER, ranks)[1]
+            cpu_baselines["mpi"] = {"Mpixel/s": H * W / (ms_mpi * 1e-3) / 1e6, "cores": ranks,
+                                    "note": "reference fft_mpi.cpp over the single-node MPI stand-in (oracle/mpi_standin)"}
+        cpu_baselines["sample"] = "1 image of %dx%dx3 per mode, reference sources compiled unmodified (oracle/_ref)" % (H, W)
 
     line = {
         "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
@@ -580,6 +839,12 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
     }
+    if cpu_baselines:
+        line["cpu_baselines"] = cpu_baselines
+    if side:
+        line["side"] = side
+    if sharded:
+        line["sharded"] = sharded
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -443,3 +443,36 @@ def test_many_tiny_images_grid_cap(gpu, oracle):
         planes = [imgs[i, :, :, c].astype(np.float32) * np.float32(1.0 / 255.0) for c in range(3)]
         want, _ = oracle.restore_image_u8(planes, psf, K)
         assert np.abs(out[i].astype(int) - want.astype(int)).max() <= 1
+
+
+def test_full_size_16384_against_serial_oracle(gpu, oracle):
+    """BASELINE configs[4] at full size, one colour plane against the serial restatement of fft_serial.cpp:141-261 (the
+    long-row kernels, the K x 2048 column blocks and the half-plane path all at their real geometry): forward and filtered
+    spectra within 1e-4 relative L2, 8-bit plane within +-1 LSB on >= 99.9 % of the pixels, exact counts printed.  About two
+    minutes of serial CPU work."""
+    H = W = 16384
+    img = oracle.synth_image_u8(4, 0, H, W)                 # (3, H, W)
+    psf = oracle.port().motion_psf(50, 30.0)
+    plane0 = img[0].astype(np.float32) * np.float32(1.0 / 255.0)
+    res = oracle.port().wiener_deblur(plane0, psf, K, want=("G", "F", "norm"))
+    want_u8 = oracle.port().pack_u8(res["norm"])
+    with gpu.Plan(H, W, 3) as p:
+        p.set_psf_motion(50, 30.0, K)
+        G = p.forward_spectrum(plane0)
+        eg = rel_l2(G, res["G"])
+        del G
+        F = p.filtered_spectrum(plane0)
+        ef = rel_l2(F, res["F"])
+        del F
+        got = p.restore_images_u8(np.ascontiguousarray(np.transpose(img, (1, 2, 0)))[None])[0]
+        half = p.half_plane
+    print("16384^2: forward spectrum rel-L2 %.3g, filtered spectrum rel-L2 %.3g (gate %g), half-plane path for plane 2: %s"
+          % (eg, ef, SPECTRUM_TOL, half))
+    assert eg < SPECTRUM_TOL and ef < SPECTRUM_TOL
+    check_u8(got[:, :, 0], want_u8)
+    # planes 1 and 2 (plane 2 takes the half-plane path) against the reference's own openmp build when it is there
+    if oracle.have_ref():
+        oracle.ref().set_threads(os.cpu_count() or 1)
+        for c in (1, 2):
+            norm = oracle.ref().wiener(img[c].astype(np.float32) * np.float32(1.0 / 255.0), psf, K, "openmp")
+            check_u8(got[:, :, c], oracle.port().pack_u8(norm))
