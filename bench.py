@@ -36,6 +36,31 @@ K_WIENER = 0.01
 CONTRACT_BYTES_PER_CHANNEL_PIXEL = 53.0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The reference's translation units (oracle/_ref) print their profile blocks on stdout from C++; the contract is ONE JSON
+    line on stdout.  Keep the real stdout aside for that line and send everything else (C and Python) to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
+def _trace(msg):
+    """FDR_BENCH_TRACE=1: stage markers on stderr (debugging aid)."""
+    if os.environ.get("FDR_BENCH_TRACE"):
+        print("[bench %.1fs] %s" % (time.perf_counter(), msg), file=sys.stderr, flush=True)
+
+
 def _load(name, path):
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
@@ -172,7 +197,7 @@ def run_reference(args):
                                    % (sample, H, W, mode, mode)},
         "e2e": {"value": mpx, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -439,7 +464,7 @@ def run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H
                      "phases_ms": r["phases_ms_serial_schedule"], "nvlink": r["nvlink"], "pipeline": r["contract53"]},
         "cpu_baseline": None, "parity": r["parity"], "sharded": r,
     }
-    print(json.dumps(line))
+    emit(line)
     dist.destroy_process_group()
     return 0
 
@@ -449,47 +474,18 @@ def side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, ou
     oracle/_ref/libref_gpu.so) through its 3-plane host boundary as gpu.cpp:96-105 times it, beside this library through the
     same boundary; (2) an eager torch.fft (cuFFT) pipeline with the same two-planes-per-transform packing, device resident.
     Side comparisons only: neither is on the product path."""
-    import ctypes as C
-    import numpy as np
     out = {}
-    O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
-    psf = O.port().motion_psf(plen, pang)
     lp = os.path.join(ROOT, "oracle", "_ref", "libref_gpu.so")
     try:
         if os.path.exists(lp):
-            lib = C.CDLL(lp)
-            fpp = C.POINTER(C.c_float)
-            lib.ref_gpu_restore.restype = C.c_double
-            lib.ref_gpu_restore.argtypes = [C.c_int, fpp, C.c_int, C.c_int, C.c_int, fpp, C.c_int, C.c_int, C.c_float]
-            planes = np.stack([O.synth_image_u8(3, 0, H, W)[c].astype(np.float32) / np.float32(255) for c in range(3)])
-            S = psf.shape[0]
-            devnull = os.open(os.devnull, os.O_WRONLY)
-            saved = os.dup(1)
-            sys.stdout.flush()
-            os.dup2(devnull, 1)  # the reference prints its profile block on every call
-            try:
-                buf = planes.copy()
-                lib.ref_gpu_restore(0, buf.ctypes.data_as(fpp), 3, H, W, psf.ctypes.data_as(fpp), S, S, K_WIENER)
-                ts = []
-                for _ in range(3):
-                    buf = planes.copy()
-                    ts.append(lib.ref_gpu_restore(0, buf.ctypes.data_as(fpp), 3, H, W, psf.ctypes.data_as(fpp), S, S, K_WIENER))
-            finally:
-                sys.stdout.flush()
-                os.dup2(saved, 1)
-                os.close(devnull)
-            with fdr.Plan(H, W, 1) as p1:
-                p1.set_psf(psf, K_WIENER)
-                p1.restore_planes(list(planes))
-                to = []
-                for _ in range(3):
-                    t0 = time.perf_counter()
-                    p1.restore_planes(list(planes))
-                    to.append((time.perf_counter() - t0) * 1e3)
-            out["reference_gpu_mode"] = {"ms_per_image": min(ts), "Mpixel/s": H * W / (min(ts) * 1e-3) / 1e6,
-                                         "this_library_same_boundary_ms": min(to), "speedup": min(ts) / min(to),
-                                         "what": "fft_gpu::wienerDeblur_RGB_optimized of the reference (fft_gpu.cu:279-394, unmodified, sm_100a) "
-                                                 "on one %dx%dx3 image, 3 f32 host planes in and out, wall clock as gpu.cpp:96-105" % (H, W)}
+            # own process: the reference exits on any CUDA error (CHECK_CUDA, fft_gpu.cu:59-66)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "side_refgpu.py"), str(H), str(W), str(plen), str(pang)],
+                               capture_output=True, text=True, timeout=180)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and last:
+                out["reference_gpu_mode"] = json.loads(last[-1])
+            else:
+                out["reference_gpu_mode"] = {"unavailable": "rc=%d %s" % (r.returncode, (r.stderr or r.stdout)[-300:])}
     except Exception as e:
         out["reference_gpu_mode"] = {"unavailable": str(e)[:200]}
     try:
@@ -555,6 +551,7 @@ def main():
     ap.add_argument("--sharded-steps", type=int, default=20)
     ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
@@ -682,6 +679,7 @@ def main():
                            "note": "end to end is bound by the host link: pinned H2D and D2H run concurrently with the kernels; with N ranks "
                                    "on one host the copies share the host's memory and PCIe root complexes, so the per-GPU rate drops as N grows"}
 
+    _trace('timed region + e2e done')
     padded = plan.padded
     check_idx = sorted({0, max(0, B // 2 - 1), B - 1})   # first, middle, last image of the batch
     got = {i: d_out[i].cpu().numpy() for i in check_idx} if rank == 0 else {}
@@ -689,6 +687,7 @@ def main():
     side = None
     if rank == 0 and world == 1 and not args.no_side:
         side = side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, value)
+    _trace('side done')
     # ---- BASELINE configs[4] inside the same line when N > 1: one 16384^2 RGB image row-sharded over all ranks ----
     sharded = None
     if world > 1 and not args.no_sharded and args.workload == "batch256x2048":
@@ -706,6 +705,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    _trace('sharded leg done')
     # ---- roofline of the dominant kernel (live CUDA-event durations of this run) ----
     peak, peak_src = measured_peak_gbs()
     dom = max(ktimes, key=lambda k: ktimes[k]["ms"])
@@ -764,6 +764,7 @@ def main():
         },
     }
 
+    _trace('roofline done')
     # ---- parity spot check + CPU baseline on a bounded sample (rank 0 only) ----
     O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
     psf = O.port().motion_psf(plen, pang)
@@ -808,6 +809,7 @@ def main():
                 d = np.abs(got[i].astype(np.int16) - want.astype(np.int16))
                 parity["more_images"].append({"image": first_image + i, "exact": int((d == 0).sum()), "off_by_1": int((d == 1).sum()),
                                               "off_by_more": int((d > 1).sum()), "frac_within_1": float((d <= 1).mean())})
+    _trace('parity + serial baseline done')
     cpu_baselines = None
     if want_cpu and O.have_ref() and not args.no_side:
         # north_star: serial, OpenMP (and the SIMD and MPI modes) timed in the same run, one image each, on this host
@@ -825,6 +827,7 @@ def main():
                                     "note": "reference fft_mpi.cpp over the single-node MPI stand-in (oracle/mpi_standin)"}
         cpu_baselines["sample"] = "1 image of %dx%dx3 per mode, reference sources compiled unmodified (oracle/_ref)" % (H, W)
 
+    _trace('cpu baselines done')
     line = {
         "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
         "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -845,7 +848,7 @@ def main():
         line["side"] = side
     if sharded:
         line["sharded"] = sharded
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
