@@ -22,6 +22,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# the sharded driver keeps compute, link and barrier streams apart: give every stream its own hardware queue
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 PKG = os.path.join(ROOT, "parallel-implementation-of-frequency-domain-image-restoration-using-fft_b200")
 
 WORKLOADS = {
@@ -290,28 +292,32 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
     dist.barrier()
 
     # per-phase device times of the serial schedule (separate pass; the timed region above runs the pipelined driver)
-    ph = np.zeros(5)
+    ph = np.zeros(7)
     reps = 3
     for _ in range(reps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(10)]
         ev[0].record(stream)
         back.phase1(d_in.data_ptr(), sh)
         ev[1].record(stream)
-        drv.barrier(set_index=13, stream=sh)
+        back.exchange1(sh)
         ev[2].record(stream)
-        back.phase2(sh)
+        drv.barrier(set_index=13, stream=sh)
         ev[3].record(stream)
-        drv.barrier(set_index=14, stream=sh)
+        back.phase2(sh)
         ev[4].record(stream)
-        back.phase3(sh)
+        back.exchange3(sh)
         ev[5].record(stream)
-        drv._reduce_minmax()
+        drv.barrier(set_index=14, stream=sh)
         ev[6].record(stream)
-        back.phase4(d_out.data_ptr(), sh)
+        back.phase3(sh)
         ev[7].record(stream)
+        drv._reduce_minmax()
+        ev[8].record(stream)
+        back.phase4(d_out.data_ptr(), sh)
+        ev[9].record(stream)
         torch.cuda.synchronize()
-        ph += np.array([ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3]), ev[4].elapsed_time(ev[5]), ev[6].elapsed_time(ev[7]),
-                        ev[0].elapsed_time(ev[7])])
+        ph += np.array([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[3].elapsed_time(ev[4]), ev[4].elapsed_time(ev[5]),
+                        ev[6].elapsed_time(ev[7]), ev[8].elapsed_time(ev[9]), ev[0].elapsed_time(ev[9])])
     pt = torch.tensor(ph / reps, dtype=torch.float64, device=dev)
     dist.all_reduce(pt, op=dist.ReduceOp.MAX)
     ph = [float(x) for x in pt.tolist()]
@@ -410,6 +416,7 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
     timed_out = back.sync_timed_out(sh)
     launches = back.last_launch_count()
     half = back.half_plane
+    back_staged = bool(getattr(back, "staged", False))
     Rp, Cp = back.padded_rows, back.padded_cols
     back.close()
     peak, peak_src = measured_peak_gbs()
@@ -417,19 +424,23 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
     col_bytes_px = 56.0 if Rp >= 8192 else 24.0                       # K x 2048 block scheme: three sweeps
     bytes_p2 = col_bytes_px * Rp * (Cp / world) * planes_c            # per rank
     nvlink_bytes_phase = 8.0 * Rp * Cp / world * (world - 1) / world * planes_c   # per rank, per exchange
-    names = ["phase1_rows_fwd_scatter", "phase2_cols_wiener", "phase3_gather_rows_inv", "phase4_pack"]
+    staged = back_staged
+    names = ["phase1_rows_fwd", "exchange1_push", "phase2_cols_wiener", "exchange3_push", "phase3_rows_inv", "phase4_pack"]
+    t_x1 = ph[1] if staged else ph[0]   # fused form: the exchange is inside the row pass
+    t_x3 = ph[3] if staged else ph[4]
     chan_px = H * W * 3
     res = {
         "workload": "rgb16384" if H == 16384 else "%dx%dx3" % (H, W), "image": [H, W, 3], "n_gpus": world,
         "ms_per_step": ms_step, "value": H * W / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s", "steps": steps, "warmup": warmup,
-        "scaling": "strong", "half_plane": bool(half), "peer_sync": bool(drv.peer_sync), "unit_pipeline": True,
+        "scaling": "strong", "half_plane": bool(half), "staged_exchanges": staged, "peer_sync": bool(drv.peer_sync),
+        "driver": "fdr_shard_restore_rows (native, pipelined over the colour planes)" if (drv.peer_sync and drv.native) else "python unit pipeline",
         "phases_ms_serial_schedule": dict(zip(names + ["total"], ph)),
-        "phase2_hbm": {"bytes_per_gpu": bytes_p2, "GBps": bytes_p2 / (ph[1] * 1e-3) / 1e9 if ph[1] > 0 else None,
-                       "frac_of_peak": bytes_p2 / (ph[1] * 1e-3) / 1e9 / peak if ph[1] > 0 else None, "peak": peak, "peak_source": peak_src},
+        "phase2_hbm": {"bytes_per_gpu": bytes_p2, "GBps": bytes_p2 / (ph[2] * 1e-3) / 1e9 if ph[2] > 0 else None,
+                       "frac_of_peak": bytes_p2 / (ph[2] * 1e-3) / 1e9 / peak if ph[2] > 0 else None, "peak": peak, "peak_source": peak_src},
         "nvlink": {"bytes_per_gpu_per_exchange": nvlink_bytes_phase, "measured_peer_GBps": 770.0,
                    "bound_ms_both_exchanges": 2 * nvlink_bytes_phase / 770e9 * 1e3,
-                   "phase1_GBps": nvlink_bytes_phase / (ph[0] * 1e-3) / 1e9 if ph[0] > 0 else None,
-                   "phase3_GBps": nvlink_bytes_phase / (ph[2] * 1e-3) / 1e9 if ph[2] > 0 else None},
+                   "exchange1_GBps": nvlink_bytes_phase / (t_x1 * 1e-3) / 1e9 if t_x1 > 0 else None,
+                   "exchange3_GBps": nvlink_bytes_phase / (t_x3 * 1e-3) / 1e9 if t_x3 > 0 else None},
         "contract53": {"bytes_per_channel_pixel": CONTRACT_BYTES_PER_CHANNEL_PIXEL,
                        "GBps_aggregate": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (ms_step * 1e-3) / 1e9,
                        "frac_of_aggregate_peak_contract53": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (ms_step * 1e-3) / 1e9 / (peak * world),

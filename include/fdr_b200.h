@@ -206,6 +206,20 @@ int fdr_shard_set_row_ctas(fdr_shard* shard, int ctas);
 /* enabled: the vector of fdr_shard_minmax_device holds (min, -max) per plane so that ONE all-reduce(MIN) over all of it
  * folds both extrema; phase 4 undoes the sign.  Default off (column 0 MIN, column 1 MAX). */
 int fdr_shard_set_minmax_negated(fdr_shard* shard, int enabled);
+/* STAGED mode (the default in half-plane mode on more than one rank; FDR_SHARD_STAGED=0 keeps the fused stores/loads): phase 1
+ * and phase 3 work on LOCAL staging planes and these two calls move the column blocks between the ranks -- exchange 1 after
+ * phase 1 (row spectra -> the column owners' slabs), exchange 3 after phase 2 (filtered columns -> the row owners' staging
+ * planes) -- as plain stores over NVLink from a few persistent CTAs (fdr_shard_set_link_ctas, default 32), so a transfer
+ * runs beside the passes of other units instead of holding every SM.  A barrier must follow each exchange.  No-ops when the
+ * shard is not staged.  They are the MPI_Alltoallv calls of fft_mpi.cpp:284-307. */
+int fdr_shard_exchange1(fdr_shard* shard, int unit_first, int unit_count, void* stream);
+int fdr_shard_exchange3(fdr_shard* shard, int unit_first, int unit_count, void* stream);
+int fdr_shard_staged(const fdr_shard* shard, int* enabled);
+int fdr_shard_set_link_ctas(fdr_shard* shard, int ctas);
+/* The whole restoration of this rank's rows in one call, pipelined over the units: passes on a compute stream, exchanges
+ * and barriers on two high-priority streams, events in between; ordered after / before `stream`.  Collective: every rank
+ * calls it.  Needs the peer-memory barriers below (no NCCL / MPI on the per-image path).  mpi.cpp:95-111. */
+int fdr_shard_restore_rows(fdr_shard* shard, const void* d_in_rows_u8, void* d_out_rows_u8, void* stream);
 /* Cross-rank synchronisation through flags in peer memory (the slab allocation carries them, so fdr_shard_set_peers is all
  * the set-up they need).  They replace the synchronisation implied by MPI_Alltoallv (fft_mpi.cpp:170-279) and keep NCCL /
  * MPI out of the per-image path.  fdr_shard_barrier: stream-ordered barrier; every rank calls it with the same `set`

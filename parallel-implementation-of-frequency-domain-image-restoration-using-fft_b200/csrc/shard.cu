@@ -71,6 +71,17 @@ struct fdr_shard {
     int minmax_neg = 0;         // mmf holds (min, -max): one all-reduce(MIN) folds both
     // peer synchronisation area at the tail of the slab allocation (so the slab's IPC handle covers it): barrier flags
     // [SYNC_SETS][FDR_MAX_PEERS] u32, then the extrema mailbox [2][FDR_MAX_PEERS][C][2] f32, then one status word
+    // STAGED mode (half-plane mode on more than one rank; FDR_SHARD_STAGED=0 keeps the fused form): the row passes work on
+    // LOCAL full-width half planes [C][Rl][Cp/2] (+ Nyquist [C][Rl]) and a separate link kernel on a few SMs pushes the
+    // column blocks to / from the peers' slabs, so the NVLink-bound transfers run beside the HBM-bound passes of other units
+    // instead of holding every SM (exchange1 / exchange3 below).  The staging planes live in the same allocation as the slab
+    // because the peers store into them in exchange 3.
+    bool staged = false;
+    size_t stage_off = 0, stage_nyq_off = 0;   // element offsets inside the slab allocation
+    int link_ctas = 32;
+    // native pipelined driver (fdr_shard_restore_rows): compute / link / barrier streams and the events between them
+    cudaStream_t st_cmp = nullptr, st_link = nullptr, st_bar = nullptr;
+    std::vector<cudaEvent_t> ev;               // [7 * units + 2]
     size_t sync_off = 0;        // element (float2) offset of the area inside the slab allocation
     unsigned int epoch[16] = {};  // barriers issued so far per flag set (every rank issues the same sequence)
     unsigned int mm_epoch = 0;
@@ -165,6 +176,83 @@ void fill_half_peers(const fdr_shard* s, RowPassArgs& r) {
     r.hp_plane = (long long)s->Rp * s->Ch;
     r.nyq_world = s->world;
     r.nyq_plane = s->Rp;
+}
+
+// staged mode: the row passes see ONE owner holding all Cp/2 columns of the local rows (row index = local row)
+void fill_half_staged(const fdr_shard* s, RowPassArgs& r) {
+    r.hp_peers[0] = s->slab.p + s->stage_off;
+    r.nyq_peers[0] = s->slab.p + s->stage_nyq_off;
+    r.hp_shift = ilog2(s->Cp / 2);
+    r.hp_plane = (long long)s->Rl * (s->Cp / 2);
+    r.nyq_world = 1;
+    r.nyq_plane = s->Rl;
+    r.row0 = 0;
+}
+
+// ---- link kernel: the all-to-all of the reference's MPI_Alltoallv (fft_mpi.cpp:170-279) as plain stores into peer memory,
+// issued by a FEW persistent CTAs.  A job copies `rows` rows of `row_elems` complex values between two pitched planes. ----
+struct PushJob {
+    const float2* src;
+    float2* dst;
+    long long src_pitch, dst_pitch;   // elements
+    int rows, row_shift;              // row_elems = 1 << row_shift
+};
+struct PushArgs {
+    PushJob big[FDR_MAX_PEERS];       // equal shapes, one per destination rank
+    int nbig, nbig_shift;             // nbig = 1 << nbig_shift (the world size, or 1)
+    const float2* small_src[FDR_MAX_PEERS];   // contiguous runs (Nyquist vectors)
+    float2* small_dst[FDR_MAX_PEERS];
+    int small_n[FDR_MAX_PEERS];
+    int nsmall;
+};
+// V = elements per access (2: 16-byte vectors, needs row_elems even and 16-byte aligned planes; 1 otherwise).  Work items are
+// interleaved over the destinations (item = vector * nbig + job) so that every NVLink carries traffic all the time.
+template <int V> __global__ void __launch_bounds__(512) peer_push_kernel(PushArgs a) {
+    using Vec = typename std::conditional<V == 2, float4, float2>::type;
+    if (blockIdx.x == 0) {
+        for (int j = 0; j < a.nsmall; ++j)
+            for (int i = threadIdx.x; i < a.small_n[j]; i += blockDim.x) a.small_dst[j][i] = a.small_src[j][i];
+    }
+    if (a.nbig == 0) return;
+    const int vshift = a.big[0].row_shift - (V == 2 ? 1 : 0);      // vectors per row = 1 << vshift
+    const long long per_job = (long long)a.big[0].rows << vshift;
+    const long long total = per_job * a.nbig;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr int U = 8;
+    long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i0 < total; i0 += stride * U) {
+        Vec v[U];
+        long long off[U];
+        int jb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            jb[u] = -1;
+            if (i < total) {
+                const int j = (int)(i & (a.nbig - 1));
+                const long long w = i >> a.nbig_shift;
+                const long long row = w >> vshift, col = w & ((1LL << vshift) - 1);
+                jb[u] = j;
+                off[u] = row * a.big[j].dst_pitch + col * V;
+                v[u] = *reinterpret_cast<const Vec*>(a.big[j].src + row * a.big[j].src_pitch + col * V);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (jb[u] >= 0) *reinterpret_cast<Vec*>(a.big[jb[u]].dst + off[u]) = v[u];
+    }
+}
+cudaError_t launch_push(PushArgs& a, int ctas, cudaStream_t st) {
+    a.nbig_shift = a.nbig > 0 ? ilog2(a.nbig) : 0;
+    bool v2 = a.nbig > 0 && a.big[0].row_shift >= 1;
+    for (int j = 0; j < a.nbig && v2; ++j)
+        v2 = ((reinterpret_cast<uintptr_t>(a.big[j].src) | reinterpret_cast<uintptr_t>(a.big[j].dst)) % 16 == 0) &&
+             a.big[j].src_pitch % 2 == 0 && a.big[j].dst_pitch % 2 == 0;
+    if (v2)
+        peer_push_kernel<2><<<ctas, 512, 0, st>>>(a);
+    else
+        peer_push_kernel<1><<<ctas, 512, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 int build_wiener(fdr_shard* s) {
@@ -311,7 +399,17 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
     if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "shard setup: %s", cudaGetErrorString(e));
     if (s->half) {
         s->nyq_off = (size_t)channels * Rp * s->Ch;
-        s->sync_off = (s->nyq_off + (size_t)channels * Rp + 31) & ~(size_t)31;
+        size_t end = s->nyq_off + (size_t)channels * Rp;
+        const char* sg = getenv("FDR_SHARD_STAGED");
+        s->staged = world > 1 && !(sg && atoi(sg) == 0);
+        if (s->staged) {
+            s->stage_off = (end + 31) & ~(size_t)31;
+            s->stage_nyq_off = s->stage_off + (size_t)channels * s->Rl * (Cp / 2);
+            end = s->stage_nyq_off + (size_t)channels * s->Rl;
+        }
+        const char* lc = getenv("FDR_SHARD_LINK_CTAS");
+        if (lc && atoi(lc) > 0) s->link_ctas = atoi(lc);
+        s->sync_off = (end + 31) & ~(size_t)31;
         if (rc == FDR_OK) rc = s->slab.ensure(s->sync_off + sync_area_elems(channels));
         if (rc == FDR_OK) rc = s->wiener.ensure((size_t)Rp * s->Ch);
         if (rc == FDR_OK) rc = s->wiener_nyq.ensure((size_t)Rp);
@@ -327,6 +425,8 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
         cudaFuncAttributes fa;
         e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_barrier_kernel));
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_minmax_kernel));
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_push_kernel<1>));
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_push_kernel<2>));
         if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "sync kernels: %s", cudaGetErrorString(e));
     }
     if (rc == FDR_OK) {  // flags and mailboxes start at zero (before any peer can have the handle)
@@ -367,6 +467,11 @@ FDR_API int fdr_shard_destroy(fdr_shard* s) {
     s->psf.release();
     s->peers.release();
     s->self_only.release();
+    for (auto& e : s->ev)
+        if (e) cudaEventDestroy(e);
+    if (s->st_cmp) cudaStreamDestroy(s->st_cmp);
+    if (s->st_link) cudaStreamDestroy(s->st_link);
+    if (s->st_bar) cudaStreamDestroy(s->st_bar);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return FDR_OK;
@@ -495,9 +600,14 @@ FDR_API int fdr_shard_phase1_pairs(fdr_shard* s, const void* d_in_rows_u8, int p
         r.unit_base = 0;
         r.units_total = s->C;
         r.tw = s->tw_rows;
-        fill_half_peers(s, r);
-        r.row0 = s->row0;
-        r.max_ctas = s->row_ctas;
+        if (s->staged) {   // local full-width half planes; fdr_shard_exchange1 moves them
+            fill_half_staged(s, r);
+            r.hp_rows_store = s->rows_local;
+        } else {
+            fill_half_peers(s, r);
+            r.row0 = s->row0;
+            r.max_ctas = s->row_ctas;
+        }
         FDR_CUDA(launch_row_pass(r, st));
         s->launches += 1;
         return FDR_OK;
@@ -609,6 +719,10 @@ FDR_API int fdr_shard_phase3_pairs(fdr_shard* s, int pair_first, int pair_count,
     r.peer_plane = (long long)s->Rp * s->Cl;
     r.row0 = s->row0;
     r.max_ctas = s->row_ctas;
+    if (s->staged) {   // the peers' exchange 3 has filled the local staging planes
+        fill_half_staged(s, r);
+        r.max_ctas = 0;
+    }
     FDR_CUDA(launch_row_pass(r, st));
     {
         const int per = s->half ? 1 : 2;
@@ -641,6 +755,158 @@ FDR_API int fdr_shard_phase4_pack(fdr_shard* s, void* d_out_rows_u8, void* strea
     FDR_CUDA(launch_pack_u8(s->raw.p, (long long)s->rows_local * s->W, s->ss.p, static_cast<uint8_t*>(d_out_rows_u8), 1, s->C,
                             s->rows_local, s->W, st));
     s->launches += 1;
+    return FDR_OK;
+}
+
+// Staged mode only (no-ops otherwise).  exchange 1: this rank's row spectra (local staging planes, written by phase 1) ->
+// the column owners' slabs; exchange 3: this rank's filtered columns (its slab, after phase 2) -> the row owners' staging
+// planes.  Plain stores over NVLink from `link_ctas` CTAs; a barrier must follow before the data is consumed.
+FDR_API int fdr_shard_exchange1(fdr_shard* s, int unit_first, int unit_count, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    if (!s->staged) return FDR_OK;
+    if (!s->have_peers) return set_error(FDR_E_STATE, "exchange before fdr_shard_set_peers");
+    FDR_TRY(check_pairs(s, unit_first, unit_count));
+    FDR_CUDA(cudaSetDevice(s->device));
+    if (s->rows_local == 0) return FDR_OK;
+    const int Ch2 = s->Cp / 2;
+    for (int u = unit_first; u < unit_first + unit_count; ++u) {
+        PushArgs a{};
+        for (int g = 0; g < s->world; ++g) {
+            const int d = (g + s->rank) % s->world;   // start with our own block: every rank begins on a different link
+            PushJob& j = a.big[a.nbig++];
+            j.src = s->slab.p + s->stage_off + (size_t)u * s->Rl * Ch2 + (size_t)d * s->Ch;
+            j.dst = s->peer_host[(size_t)d] + (size_t)u * s->Rp * s->Ch + (size_t)s->row0 * s->Ch;
+            j.src_pitch = Ch2;
+            j.dst_pitch = s->Ch;
+            j.rows = s->rows_local;
+            j.row_shift = ilog2(s->Ch);
+        }
+        const int owner = u % s->world;
+        a.small_src[0] = s->slab.p + s->stage_nyq_off + (size_t)u * s->Rl;
+        a.small_dst[0] = s->peer_host[(size_t)owner] + s->nyq_off + (size_t)u * s->Rp + s->row0;
+        a.small_n[0] = s->rows_local;
+        a.nsmall = 1;
+        FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
+        s->launches += 1;
+    }
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_exchange3(fdr_shard* s, int unit_first, int unit_count, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    if (!s->staged) return FDR_OK;
+    if (!s->have_peers) return set_error(FDR_E_STATE, "exchange before fdr_shard_set_peers");
+    FDR_TRY(check_pairs(s, unit_first, unit_count));
+    FDR_CUDA(cudaSetDevice(s->device));
+    const int Ch2 = s->Cp / 2;
+    for (int u = unit_first; u < unit_first + unit_count; ++u) {
+        PushArgs a{};
+        for (int g = 0; g < s->world; ++g) {
+            const int d = (g + s->rank) % s->world;
+            PushJob& j = a.big[a.nbig++];
+            j.src = s->slab.p + (size_t)u * s->Rp * s->Ch + (size_t)d * s->Rl * s->Ch;
+            j.dst = s->peer_host[(size_t)d] + s->stage_off + (size_t)u * s->Rl * Ch2 + (size_t)s->rank * s->Ch;
+            j.src_pitch = s->Ch;
+            j.dst_pitch = Ch2;
+            j.rows = s->Rl;
+            j.row_shift = ilog2(s->Ch);
+            if (u % s->world == s->rank) {   // the Nyquist column of this unit lives here
+                a.small_src[a.nsmall] = s->slab.p + s->nyq_off + (size_t)u * s->Rp + (size_t)d * s->Rl;
+                a.small_dst[a.nsmall] = s->peer_host[(size_t)d] + s->stage_nyq_off + (size_t)u * s->Rl;
+                a.small_n[a.nsmall] = s->Rl;
+                a.nsmall++;
+            }
+        }
+        FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
+        s->launches += 1;
+    }
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_staged(const fdr_shard* s, int* enabled) {
+    if (!s || !enabled) return set_error(FDR_E_INVALID, "bad arguments");
+    *enabled = s->staged ? 1 : 0;
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_set_link_ctas(fdr_shard* s, int ctas) {
+    if (!s || ctas < 1) return set_error(FDR_E_INVALID, "bad arguments");
+    s->link_ctas = ctas;
+    return FDR_OK;
+}
+
+// The whole restoration of this rank's rows as a pipeline over the units (planes), issued in one call: compute passes on one
+// stream, link kernels and barriers on two high-priority streams, events in between -- unit u's transfers run beside the
+// passes of the other units.  Every rank must call it (it contains the cross-rank barriers of fdr_shard_barrier).
+// Replaces the per-channel loop of mpi.cpp:95-111 with its blocking MPI_Alltoallv calls (fft_mpi.cpp:284-307).
+FDR_API int fdr_shard_restore_rows(fdr_shard* s, const void* d_in_rows_u8, void* d_out_rows_u8, void* stream) {
+    if (!s) return set_error(FDR_E_INVALID, "shard is NULL");
+    if (!s->have_peers || !s->have_wiener) return set_error(FDR_E_STATE, "set peers and PSF before restoring");
+    if (2 * s->units > SYNC_SETS - 3) return set_error(FDR_E_INVALID, "too many units (%d) for the pipelined driver", s->units);
+    FDR_CUDA(cudaSetDevice(s->device));
+    const int U = s->units;
+    if (!s->st_cmp) {
+        int lo = 0, hi = 0;
+        FDR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        FDR_CUDA(cudaStreamCreateWithPriority(&s->st_cmp, cudaStreamNonBlocking, lo));
+        FDR_CUDA(cudaStreamCreateWithPriority(&s->st_link, cudaStreamNonBlocking, hi));
+        FDR_CUDA(cudaStreamCreateWithPriority(&s->st_bar, cudaStreamNonBlocking, hi));
+        s->ev.resize((size_t)7 * U + 2);
+        for (auto& e : s->ev) FDR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t caller = pick(s, stream);
+    auto E = [&](int kind, int u) { return s->ev[(size_t)kind * U + u]; };   // kinds 0..6
+    cudaEvent_t ev_fork = s->ev[(size_t)7 * U], ev_join = s->ev[(size_t)7 * U + 1];
+    FDR_CUDA(cudaEventRecord(ev_fork, caller));
+    FDR_CUDA(cudaStreamWaitEvent(s->st_cmp, ev_fork, 0));
+    FDR_CUDA(cudaStreamWaitEvent(s->st_link, ev_fork, 0));
+    FDR_CUDA(cudaStreamWaitEvent(s->st_bar, ev_fork, 0));
+    const bool one = s->world == 1;
+    for (int u = 0; u < U; ++u) {   // rows forward
+        FDR_TRY(fdr_shard_phase1_pairs(s, d_in_rows_u8, u, 1, s->st_cmp));
+        FDR_CUDA(cudaEventRecord(E(0, u), s->st_cmp));
+    }
+    if (!one) {
+        for (int u = 0; u < U; ++u) {   // exchange 1 + barrier
+            if (s->staged) {
+                FDR_CUDA(cudaStreamWaitEvent(s->st_link, E(0, u), 0));
+                FDR_TRY(fdr_shard_exchange1(s, u, 1, s->st_link));
+                FDR_CUDA(cudaEventRecord(E(1, u), s->st_link));
+                FDR_CUDA(cudaStreamWaitEvent(s->st_bar, E(1, u), 0));
+            } else {
+                FDR_CUDA(cudaStreamWaitEvent(s->st_bar, E(0, u), 0));
+            }
+            FDR_TRY(fdr_shard_barrier(s, 2 * u, s->st_bar));
+            FDR_CUDA(cudaEventRecord(E(2, u), s->st_bar));
+        }
+    }
+    for (int u = 0; u < U; ++u) {   // columns
+        if (!one) FDR_CUDA(cudaStreamWaitEvent(s->st_cmp, E(2, u), 0));
+        FDR_TRY(fdr_shard_phase2_pairs(s, u, 1, s->st_cmp));
+        FDR_CUDA(cudaEventRecord(E(3, u), s->st_cmp));
+    }
+    if (!one) {
+        for (int u = 0; u < U; ++u) {   // exchange 3 + barrier
+            if (s->staged) {
+                FDR_CUDA(cudaStreamWaitEvent(s->st_link, E(3, u), 0));
+                FDR_TRY(fdr_shard_exchange3(s, u, 1, s->st_link));
+                FDR_CUDA(cudaEventRecord(E(4, u), s->st_link));
+                FDR_CUDA(cudaStreamWaitEvent(s->st_bar, E(4, u), 0));
+            } else {
+                FDR_CUDA(cudaStreamWaitEvent(s->st_bar, E(3, u), 0));
+            }
+            FDR_TRY(fdr_shard_barrier(s, 2 * u + 1, s->st_bar));
+            FDR_CUDA(cudaEventRecord(E(5, u), s->st_bar));
+        }
+    }
+    for (int u = 0; u < U; ++u) {   // rows inverse
+        if (!one) FDR_CUDA(cudaStreamWaitEvent(s->st_cmp, E(5, u), 0));
+        FDR_TRY(fdr_shard_phase3_pairs(s, u, 1, s->st_cmp));
+    }
+    if (!one) FDR_TRY(fdr_shard_minmax_allreduce(s, s->st_cmp));
+    FDR_TRY(fdr_shard_phase4_pack(s, d_out_rows_u8, s->st_cmp));
+    FDR_CUDA(cudaEventRecord(ev_join, s->st_cmp));
+    FDR_CUDA(cudaStreamWaitEvent(caller, ev_join, 0));
     return FDR_OK;
 }
 

@@ -100,6 +100,11 @@ def lib():
             "fdr_shard_half_plane": [vp, C.POINTER(i)],
             "fdr_shard_set_row_ctas": [vp, i],
             "fdr_shard_set_minmax_negated": [vp, i],
+            "fdr_shard_exchange1": [vp, i, i, vp],
+            "fdr_shard_exchange3": [vp, i, i, vp],
+            "fdr_shard_staged": [vp, C.POINTER(i)],
+            "fdr_shard_set_link_ctas": [vp, i],
+            "fdr_shard_restore_rows": [vp, vp, vp, vp],
             "fdr_shard_barrier": [vp, i, vp],
             "fdr_shard_minmax_allreduce": [vp, vp],
             "fdr_shard_sync_status": [vp, vp, C.POINTER(i)],
@@ -357,6 +362,26 @@ class Shard:
     def set_minmax_negated(self, on=True):
         _check(lib().fdr_shard_set_minmax_negated(self.h, int(on)))
         self.minmax_negated = bool(on)
+
+    @property
+    def staged(self):
+        v = C.c_int(0)
+        _check(lib().fdr_shard_staged(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def set_link_ctas(self, n):
+        _check(lib().fdr_shard_set_link_ctas(self.h, int(n)))
+
+    def exchange1(self, stream=0, pair=None):
+        first, count = (0, self.npairs) if pair is None else (pair, 1)
+        _check(lib().fdr_shard_exchange1(self.h, first, count, stream))
+
+    def exchange3(self, stream=0, pair=None):
+        first, count = (0, self.npairs) if pair is None else (pair, 1)
+        _check(lib().fdr_shard_exchange3(self.h, first, count, stream))
+
+    def restore_rows_native(self, d_in_rows, d_out_rows, stream=0):
+        _check(lib().fdr_shard_restore_rows(self.h, d_in_rows, d_out_rows, stream))
 
     def peer_barrier(self, set_index, stream=0):
         _check(lib().fdr_shard_barrier(self.h, int(set_index), stream))

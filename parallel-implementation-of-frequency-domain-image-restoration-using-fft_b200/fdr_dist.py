@@ -81,6 +81,7 @@ class ShardedRestorer:
         # per-image synchronisation over peer memory instead of NCCL collectives (FDR_SHARD_PEER_SYNC=0 selects NCCL)
         self.peer_sync = (self._cuda and self.world > 1 and hasattr(backend, "peer_barrier")
                           and os.environ.get("FDR_SHARD_PEER_SYNC", "1") != "0")
+        self.native = os.environ.get("FDR_SHARD_NATIVE", "1") != "0"   # pipelined driver inside the library
 
     def set_psf_motion(self, length, angle_deg, K):
         """PSF + Wiener factor on every rank, then a cross-rank fence: the build uses the rank's column slab as
@@ -125,6 +126,13 @@ class ShardedRestorer:
         self._mm[:, 0].copy_(mn)
         self._mm[:, 1].copy_(mx)
 
+    def _exchange(self, which, stream, unit=None):
+        """Staged backends move the column blocks with their own link kernels (fdr_shard_exchange1/3); fused ones did it
+        inside the row passes."""
+        f = getattr(self.b, "exchange1" if which == 1 else "exchange3", None)
+        if f is not None:
+            f(stream, pair=unit)
+
     def _restore_rows_unit_pipeline(self, d_in_rows, main):
         """Every unit on its own side stream, phases interleaved across units in issue order."""
         b = self.b
@@ -139,8 +147,10 @@ class ShardedRestorer:
                 with torch.cuda.stream(st):
                     if phase == 1:
                         b.phase1(d_in_rows, st.cuda_stream, pair=unit)
+                        self._exchange(1, st.cuda_stream, unit)
                     elif phase == 2:
                         b.phase2(st.cuda_stream, pair=unit)
+                        self._exchange(3, st.cuda_stream, unit)
                     else:
                         b.phase3(st.cuda_stream, pair=unit)
                     if phase < 3:
@@ -162,13 +172,18 @@ class ShardedRestorer:
                                  "set_stream); the cross-rank barriers are ordered against that stream only")
         elif stream is None:
             stream = 0
+        if pipeline_pairs and self.peer_sync and self.native and b.npairs <= 6 and hasattr(b, "restore_rows_native"):
+            b.restore_rows_native(d_in_rows, d_out_rows, stream)   # the whole pipeline in one native call (fdr_shard_restore_rows)
+            return
         if (pipeline_pairs and self._cuda and self.world > 1 and getattr(b, "supports_pair_pipeline", False) and 2 <= b.npairs <= 6):   # flag sets 0..11 belong to the units
             self._restore_rows_unit_pipeline(d_in_rows, cur)
         else:
             b.phase1(d_in_rows, stream)
+            self._exchange(1, stream)
             self.barrier(set_index=13, stream=stream)   # every slab has received all its columns
             b.phase2(stream)
-            self.barrier(set_index=14, stream=stream)   # every slab holds the filtered, column-inverted data
+            self._exchange(3, stream)
+            self.barrier(set_index=14, stream=stream)   # every slab / staging plane holds the filtered, column-inverted data
             b.phase3(stream)
         self._reduce_minmax()
         b.phase4(d_out_rows, stream)

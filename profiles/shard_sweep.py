@@ -38,7 +38,7 @@ def run_mode(half):
     d_out = torch.zeros_like(d_in)
     fdr.synth_rows_device_u8(d_in.data_ptr(), seed, 0, 3, H, W, first, n_rows, sh)
     torch.cuda.synchronize()
-    tag = "half" if half else "pair"
+    tag = ("staged" if back.staged else "half") if half else "pair"
 
     def timed(name, peer_sync, pipe, ctas):
         drv.peer_sync = peer_sync
@@ -59,30 +59,38 @@ def run_mode(half):
         if rank == 0:
             print("%s.%s: %.3f ms" % (tag, name, ms), flush=True)
 
+    drv.native = False
     timed("serial.nccl", False, False, 0)
     timed("serial.peer", True, False, 0)
     timed("pipe.nccl", False, True, 0)
-    for ctas in (0, 48, 64, 74, 100, 120):
+    for ctas in ((0,) if back.staged else (0, 74, 120)):
         timed("pipe.peer.ctas%d" % ctas, True, True, ctas)
     back.set_row_ctas(0)
     drv.peer_sync = True
+    drv.native = True
+    for lc in ((8, 16, 24, 32, 48, 64) if back.staged else (32,)):
+        back.set_link_ctas(lc)
+        timed("native.link%d" % lc, True, True, 0)
+    back.set_link_ctas(32)
     # per-phase times of the serial schedule
-    ph = np.zeros(5)
+    ph = np.zeros(7)
     reps = 5
     for _ in range(reps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
-        ev[0].record(stream); back.phase1(d_in.data_ptr(), sh); ev[1].record(stream)
+        ev[0].record(stream); back.phase1(d_in.data_ptr(), sh); x0 = torch.cuda.Event(enable_timing=True); x0.record(stream)
+        back.exchange1(sh); ev[1].record(stream)
         drv.barrier(set_index=13, stream=sh)
-        ev[2].record(stream); back.phase2(sh); ev[3].record(stream)
+        ev[2].record(stream); back.phase2(sh); x1 = torch.cuda.Event(enable_timing=True); x1.record(stream)
+        back.exchange3(sh); ev[3].record(stream)
         drv.barrier(set_index=14, stream=sh)
         ev[4].record(stream); back.phase3(sh); ev[5].record(stream)
         drv._reduce_minmax()
         ev[6].record(stream); back.phase4(d_out.data_ptr(), sh); ev[7].record(stream)
         torch.cuda.synchronize()
-        ph += np.array([ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3]), ev[4].elapsed_time(ev[5]), ev[6].elapsed_time(ev[7]),
-                        ev[0].elapsed_time(ev[7])])
+        ph += np.array([ev[0].elapsed_time(x0), x0.elapsed_time(ev[1]), ev[2].elapsed_time(x1), x1.elapsed_time(ev[3]),
+                        ev[4].elapsed_time(ev[5]), ev[6].elapsed_time(ev[7]), ev[0].elapsed_time(ev[7])])
     ph = [maxr(float(x) / reps) for x in ph]
-    res["variants"]["%s.phases_ms" % tag] = dict(zip(["phase1", "phase2", "phase3", "phase4", "total_serial"], ph))
+    res["variants"]["%s.phases_ms" % tag] = dict(zip(["phase1", "exchange1", "phase2", "exchange3", "phase3", "phase4", "total_serial"], ph))
     if rank == 0:
         print(tag, "phases", ph, flush=True)
     # barrier cost
@@ -120,7 +128,8 @@ def run_mode(half):
     back.close()
 
 
-for half in (True, False):
+for half, staged in ((True, True), (True, False)) + (((False, False),) if os.environ.get("SWEEP_PAIR") else ()):
+    os.environ["FDR_SHARD_STAGED"] = "1" if staged else "0"
     run_mode(half)
 if rank == 0:
     print(json.dumps(res))

@@ -7,6 +7,10 @@ import sys
 import numpy as np
 import pytest
 
+# Several shards in one process, each with three streams and spinning barrier kernels: with the default 8 hardware queues
+# unrelated streams share a queue and a waiting barrier could block the kernel it waits for.  Must be set before CUDA starts.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "parallel-implementation-of-frequency-domain-image-restoration-using-fft_b200")
 GOLDEN = os.path.join(ROOT, "tests", "golden")

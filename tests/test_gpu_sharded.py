@@ -13,17 +13,22 @@ pytestmark = pytest.mark.gpu
 K = 0.01
 
 
-def make_shards(gpu, H, W, C, world, half):
-    """half: True / False select the half-plane / plane-pair form (FDR_SHARD_HALF, read at creation)."""
-    old = os.environ.get("FDR_SHARD_HALF")
+def make_shards(gpu, H, W, C, world, half, staged=True):
+    """half: True / False select the half-plane / plane-pair form (FDR_SHARD_HALF, read at creation); staged: local staging
+    planes + link kernels (FDR_SHARD_STAGED, half-plane form on more than one rank only) or the fused stores / loads."""
+    old = {k: os.environ.get(k) for k in ("FDR_SHARD_HALF", "FDR_SHARD_STAGED")}
     os.environ["FDR_SHARD_HALF"] = "1" if half else "0"
+    os.environ["FDR_SHARD_STAGED"] = "1" if staged else "0"
     try:
-        return [gpu.Shard(H, W, C, g, world, 0) for g in range(world)]
+        shards = [gpu.Shard(H, W, C, g, world, 0) for g in range(world)]
+        assert all(s.staged == (staged and s.half_plane and world > 1) for s in shards)
+        return shards
     finally:
-        if old is None:
-            del os.environ["FDR_SHARD_HALF"]
-        else:
-            os.environ["FDR_SHARD_HALF"] = old
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
 
 
 def single_gpu(gpu, img, psf_len, psf_ang, half):
@@ -41,13 +46,13 @@ def single_gpu(gpu, img, psf_len, psf_ang, half):
             os.environ["FDR_HALF"] = old
 
 
-def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang, half=False, row_ctas=0, negated=False):
+def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang, half=False, row_ctas=0, negated=False, staged=True, native=False):
     H, W, C = images_hwc.shape
     dev = torch.device("cuda", 0)
     d_in = torch.from_numpy(images_hwc).to(dev)
     d_out = torch.zeros_like(d_in)
     dist_mod = _load("fdr_dist", PKG + "/fdr_dist.py")
-    shards = make_shards(gpu, H, W, C, world, half)
+    shards = make_shards(gpu, H, W, C, world, half, staged)
     try:
         slabs = [s.local_slab()[0] for s in shards]
         for g, s in enumerate(shards):
@@ -63,11 +68,24 @@ def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang, half=False, ro
         stream = torch.cuda.Stream(device=dev)
         sh = stream.cuda_stream
         rowbytes = W * C
+        if native:
+            # fdr_shard_restore_rows on every shard, each on its own stream: the barriers inside wait for the other shards'
+            # kernels, which this one host thread queues right behind (all kernels were loaded by an earlier serial run)
+            sts = [torch.cuda.Stream(device=dev) for _ in shards]
+            for s, st in zip(shards, sts):
+                s.restore_rows_native(d_in.data_ptr() + s.first_row * rowbytes, d_out.data_ptr() + s.first_row * rowbytes, st.cuda_stream)
+            for s, st in zip(shards, sts):
+                assert not s.sync_timed_out(st.cuda_stream)
+            return d_out.cpu().numpy(), sum(s.last_launch_count() for s in shards)
         for s in shards:
             s.phase1(d_in.data_ptr() + s.first_row * rowbytes, sh)
+        for s in shards:
+            s.exchange1(sh)
         torch.cuda.synchronize()
         for s in shards:
             s.phase2(sh)
+        for s in shards:
+            s.exchange3(sh)
         torch.cuda.synchronize()
         for s in shards:
             s.phase3(sh)
@@ -136,9 +154,9 @@ def test_sharded_half_plane_persistent_row_ctas(gpu, oracle):
     torch = pytest.importorskip("torch")
     H, W = 2048, 2048
     img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 3, H, W), (1, 2, 0)))
-    want, _ = run_emulated(gpu, torch, img, 4, 9, 30.0, half=True)
+    want, _ = run_emulated(gpu, torch, img, 4, 9, 30.0, half=True, staged=False)
     for ctas in (7, 40):
-        got, _ = run_emulated(gpu, torch, img, 4, 9, 30.0, half=True, row_ctas=ctas)
+        got, _ = run_emulated(gpu, torch, img, 4, 9, 30.0, half=True, row_ctas=ctas, staged=False)
         assert np.array_equal(got, want)
 
 
@@ -171,8 +189,10 @@ def test_sharded_per_pair_phases(gpu, oracle, H, W, world, half):
                 for s in shards:
                     if ph == 1:
                         s.phase1(d_in.data_ptr() + s.first_row * rb, sts[pair].cuda_stream, pair=pair)
+                        s.exchange1(sts[pair].cuda_stream, pair=pair)
                     elif ph == 2:
                         s.phase2(sts[pair].cuda_stream, pair=pair)
+                        s.exchange3(sts[pair].cuda_stream, pair=pair)
                     else:
                         s.phase3(sts[pair].cuda_stream, pair=pair)
             torch.cuda.synchronize()
@@ -251,3 +271,23 @@ def test_peer_barrier_and_minmax_allreduce(gpu, oracle, world, negated):
     finally:
         for s in shards:
             s.close()
+
+
+@pytest.mark.parametrize("H,W,world,C", [(200, 320, 2, 3), (256, 512, 8, 3), (1000, 70, 4, 3), (33, 70, 8, 3), (16384, 256, 8, 3),
+                                         (300, 500, 4, 4), (2048, 2048, 4, 3), (64, 64, 2, 1)])
+def test_sharded_staged_equals_fused_and_native_driver(gpu, oracle, H, W, world, C):
+    """Staged exchanges (local staging planes + link kernels, fdr_shard_exchange1/3) move the same values as the fused
+    stores / loads: bit-identical images.  The native pipelined driver (fdr_shard_restore_rows: three streams, events,
+    peer-memory barriers) gives the same bytes again; the minmax all-reduce inside it is the peer-memory one."""
+    torch = pytest.importorskip("torch")
+    img = np.ascontiguousarray(np.transpose(oracle.synth_image_u8(5, 4, H, W, channels=C), (1, 2, 0)))
+    fused, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=False)
+    staged, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=True)
+    assert np.array_equal(staged, fused), u8_gate(staged, fused)
+    for st in (True, False):
+        native, launches = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=st, native=True, negated=True)
+        assert launches > 0
+        assert np.array_equal(native, fused), (st, u8_gate(native, fused))
+    pair_native, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=False, native=True)
+    pair, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=False)
+    assert np.array_equal(pair_native, pair)
