@@ -74,6 +74,7 @@ struct RowPassArgs {
     long long peer_plane;        // elements per pair in a slab = rows_padded * (n / world)
     int row0;                    // global (padded) index of local row 0
     int max_ctas;                // > 0: scatter / gather passes run as at most this many persistent CTAs per pair
+    int prefetch_dist;           // long rows: L2 prefetch of the input of the row block this many blocks ahead (set by the launcher)
     // ---- half-plane forms (ROW_IN_ROWS2_*, ROW_OUT_HALF, ROW_IN_HALF, ROW_OUT_REAL_ROWS2): blockIdx.y counts PLANES ----
     int pair_dist;               // D: row `r` of the launch carries rows r and r + D (local indices, like `row0 + r` globally)
     int rows_in;                 // ROWS2 input: local rows present; the second row reads as zero when r + D >= rows_in

@@ -336,8 +336,60 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
     }
 }
 
+// Long rows (N >= 8192) leave room for one or two CTAs per SM, so nothing else hides the latency of a CTA's input loads.
+// Thread 0 therefore asks the L2 for the rows of the CTA that will run on this SM next (`a.prefetch_dist` row blocks ahead in
+// launch order: SMs x resident CTAs) with one cp.async.bulk.prefetch.L2 per contiguous run; those loads then hit the L2
+// while this CTA is still in its butterflies.  Local memory only (peer slabs are not cached here).
+__device__ __forceinline__ void l2_prefetch_run(const void* p, long long bytes) {
+    const unsigned long long a = reinterpret_cast<unsigned long long>(p);
+    const unsigned long long lo = (a + 15) & ~15ull, hi = (a + (unsigned long long)bytes) & ~15ull;
+    if (hi > lo) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((unsigned)(hi - lo)) : "memory");
+}
+template <int LOGN, int IN_MODE> __device__ __forceinline__ void row_prefetch_next(const RowPassArgs& a) {
+    using Gm = RowGeom<LOGN>;
+    constexpr int N = Gm::N;
+    if (threadIdx.x != 0 || a.prefetch_dist <= 0) return;
+    const int nblk = (a.nrows + Gm::RPC - 1) / Gm::RPC;
+    int rb = (int)blockIdx.x + a.prefetch_dist, y = blockIdx.y;
+    if (rb >= nblk) {   // wraps into the next pair / plane of the launch
+        rb -= nblk;
+        y += 1;
+        if (rb >= nblk || y >= (int)gridDim.y) return;
+    }
+    const int row = rb * Gm::RPC, pair = y + a.pair_base;
+    const int nr = (a.nrows - row < Gm::RPC) ? a.nrows - row : Gm::RPC;
+    if constexpr (IN_MODE == ROW_IN_COMPLEX) {
+        l2_prefetch_run(a.cin + (long long)pair * a.cplane + (long long)row * N, 8LL * N * nr);
+    } else if constexpr (IN_MODE == ROW_IN_HALF) {
+        if (a.hp_shift == LOGN - 1) {   // one owner holds whole half rows
+            const float2* base = a.hp_peers[0] + (long long)pair * a.hp_plane + ((long long)(a.row0 + row) << a.hp_shift);
+            l2_prefetch_run(base, 4LL * N * nr);
+            l2_prefetch_run(base + ((long long)a.pair_dist << a.hp_shift), 4LL * N * nr);
+        }
+    } else if constexpr (IN_MODE == ROW_IN_PAIR_U8 || IN_MODE == ROW_IN_ROWS2_U8) {
+        const bool rows2 = (IN_MODE == ROW_IN_ROWS2_U8);
+        const long long g0 = a.unit_base + (rows2 ? (long long)pair : 2LL * pair);
+        const long long img = g0 / a.channels;
+        const long long rowbytes = (long long)a.img_cols * a.channels;
+        const uint8_t* r0 = a.in_u8 + (img * a.img_rows + row) * rowbytes;
+        l2_prefetch_run(r0, rowbytes * nr);
+        if (rows2 && row + a.pair_dist < a.rows_in) l2_prefetch_run(r0 + (long long)a.pair_dist * rowbytes, rowbytes * nr);
+    } else if constexpr (IN_MODE == ROW_IN_PAIR_F32 || IN_MODE == ROW_IN_ROWS2_F32) {
+        const bool rows2 = (IN_MODE == ROW_IN_ROWS2_F32);
+        const long long u0 = a.unit_base + (rows2 ? (long long)pair : 2LL * pair);
+        const float* r0 = a.in_f32 + u0 * a.in_unit_stride + (long long)row * a.in_row_stride;
+        l2_prefetch_run(r0, 4LL * a.img_cols);
+        if (rows2) {
+            if (row + a.pair_dist < a.rows_in) l2_prefetch_run(r0 + (long long)a.pair_dist * a.in_row_stride, 4LL * a.img_cols);
+        } else if (u0 + 1 < a.units_total) {
+            l2_prefetch_run(r0 + a.in_unit_stride, 4LL * a.img_cols);
+        }
+    }
+}
+
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
 __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLOCKS) row_pass_kernel(const RowPassArgs a) {
+    if constexpr (LOGN >= 13) row_prefetch_next<LOGN, IN_MODE>(a);
     row_pass_body<LOGN, IN_MODE, OUT_MODE, CONJ>(a, blockIdx.x);
 }
 
@@ -454,6 +506,13 @@ template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row
             row_pass_persist_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
             return cudaGetLastError();
         }
+    }
+    if constexpr (LOGN >= 13) {
+        static const int pf = getenv("FDR_ROW_PREFETCH") ? atoi(getenv("FDR_ROW_PREFETCH")) : -1;   // row blocks ahead; 0 = off
+        RowPassArgs b = a;
+        b.prefetch_dist = pf >= 0 ? pf : device_sm_count() * (LOGN == 14 ? 1 : 2);
+        row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(b);
+        return cudaGetLastError();
     }
     row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
     return cudaGetLastError();

@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "capi_internal.h"
+#include "tma_util.cuh"
 
 using namespace fdr;
 
@@ -78,7 +79,7 @@ struct fdr_shard {
     // because the peers store into them in exchange 3.
     bool staged = false;
     size_t stage_off = 0, stage_nyq_off = 0;   // element offsets inside the slab allocation
-    int link_ctas = 32;
+    int link_ctas = 16;
     // native pipelined driver (fdr_shard_restore_rows): compute / link / barrier streams and the events between them
     cudaStream_t st_cmp = nullptr, st_link = nullptr, st_bar = nullptr;
     std::vector<cudaEvent_t> ev;               // [7 * units + 2]
@@ -242,8 +243,94 @@ template <int V> __global__ void __launch_bounds__(512) peer_push_kernel(PushArg
             if (jb[u] >= 0) *reinterpret_cast<Vec*>(a.big[jb[u]].dst + off[u]) = v[u];
     }
 }
+// The same jobs moved by the bulk-copy engine (cp.async.bulk global -> shared -> peer global; SASS: UBLKCP): ONE thread per CTA
+// keeps a ring of PUSH_STAGES buffers going, so a CTA has ~190 KB in flight instead of what its load/store queues hold.  Over
+// NVLink an SM's plain stores stop at ~11 GB/s (measured, 8 x B200: 64 CTAs were needed for 700 GB/s); bulk copies take the
+// SM's issue slots and registers out of the picture, which is what lets the exchange run on a few SMs beside the FFT passes.
+constexpr int PUSH_STAGE_BYTES = 32768;
+constexpr int PUSH_STAGES = 6;
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int rows_per_item, int segs_per_row, unsigned seg_bytes,
+                                                             long long items_per_job) {
+    extern __shared__ __align__(128) unsigned char push_smem[];
+    __shared__ unsigned long long bar[PUSH_STAGES];
+    if (blockIdx.x == 0 && threadIdx.x >= 32) {
+        for (int j = 0; j < a.nsmall; ++j)
+            for (int i = threadIdx.x - 32; i < a.small_n[j]; i += blockDim.x - 32) a.small_dst[j][i] = a.small_src[j][i];
+    }
+    if (threadIdx.x != 0 || a.nbig == 0) return;
+    for (int i = 0; i < PUSH_STAGES; ++i) mbar_init(&bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const long long total = items_per_job * a.nbig;
+    const long long mine = (total > blockIdx.x) ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto decode = [&](long long k, int& j, long long& row0, int& nrows, long long& c0) {
+        const long long idx = blockIdx.x + k * gridDim.x;
+        j = (int)(idx & (a.nbig - 1));
+        const long long w = idx >> a.nbig_shift;
+        const long long rg = w / segs_per_row;
+        c0 = (w - rg * segs_per_row) * (long long)(seg_bytes / 8);   // elements
+        row0 = rg * rows_per_item;
+        const long long left = a.big[j].rows - row0;
+        nrows = left < rows_per_item ? (int)left : rows_per_item;
+    };
+    auto issue_load = [&](long long k) {
+        int j, nrows;
+        long long row0, c0;
+        decode(k, j, row0, nrows, c0);
+        const int st = (int)(k % PUSH_STAGES);
+        mbar_expect_tx(&bar[st], (unsigned)nrows * seg_bytes);
+        for (int r = 0; r < nrows; ++r)
+            bulk_load_1d(push_smem + (size_t)st * PUSH_STAGE_BYTES + (size_t)r * seg_bytes, a.big[j].src + (row0 + r) * a.big[j].src_pitch + c0,
+                         seg_bytes, &bar[st]);
+    };
+    const long long pro = mine < PUSH_STAGES - 1 ? mine : PUSH_STAGES - 1;
+    for (long long k = 0; k < pro; ++k) issue_load(k);
+    for (long long k = 0; k < mine; ++k) {
+        const int st = (int)(k % PUSH_STAGES);
+        mbar_wait(&bar[st], (unsigned)((k / PUSH_STAGES) & 1));
+        int j, nrows;
+        long long row0, c0;
+        decode(k, j, row0, nrows, c0);
+        for (int r = 0; r < nrows; ++r)
+            bulk_store_1d(a.big[j].dst + (row0 + r) * a.big[j].dst_pitch + c0, push_smem + (size_t)st * PUSH_STAGE_BYTES + (size_t)r * seg_bytes,
+                          seg_bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (k + PUSH_STAGES - 1 < mine) {
+            // the buffer of item k-1 is loaded next: its stores must have finished reading shared memory
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue_load(k + PUSH_STAGES - 1);
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the kernel (and the barrier after it) ends
+}
+
 cudaError_t launch_push(PushArgs& a, int ctas, cudaStream_t st) {
     a.nbig_shift = a.nbig > 0 ? ilog2(a.nbig) : 0;
+    static const bool use_bulk = !(getenv("FDR_SHARD_BULK") && atoi(getenv("FDR_SHARD_BULK")) == 0);
+    if (use_bulk && a.nbig > 0 && a.big[0].row_shift >= 1) {
+        const long long row_bytes = 8LL << a.big[0].row_shift;
+        bool ok = true;
+        for (int j = 0; j < a.nbig && ok; ++j)
+            ok = ((reinterpret_cast<uintptr_t>(a.big[j].src) | reinterpret_cast<uintptr_t>(a.big[j].dst)) % 16 == 0) &&
+                 a.big[j].src_pitch % 2 == 0 && a.big[j].dst_pitch % 2 == 0 && a.big[j].rows == a.big[0].rows;
+        if (ok) {
+            const unsigned seg_bytes = (unsigned)(row_bytes < PUSH_STAGE_BYTES ? row_bytes : PUSH_STAGE_BYTES);
+            const int segs_per_row = (int)(row_bytes / seg_bytes);
+            int rows_per_item = PUSH_STAGE_BYTES / (int)seg_bytes;
+            if (rows_per_item > 64) rows_per_item = 64;   // tiny rows (tests): bound the copies one thread issues per item
+            const long long items_per_job = (long long)((a.big[0].rows + rows_per_item - 1) / rows_per_item) * segs_per_row;
+            const size_t smem = (size_t)PUSH_STAGES * PUSH_STAGE_BYTES;
+            cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(peer_push_bulk_kernel), smem);
+            if (e != cudaSuccess) return e;
+            long long total = items_per_job * a.nbig;
+            int grid = ctas;
+            if (total < grid) grid = total > 0 ? (int)total : 1;
+            peer_push_bulk_kernel<<<grid, 128, smem, st>>>(a, rows_per_item, segs_per_row, seg_bytes, items_per_job);
+            return cudaGetLastError();
+        }
+    }
     bool v2 = a.nbig > 0 && a.big[0].row_shift >= 1;
     for (int j = 0; j < a.nbig && v2; ++j)
         v2 = ((reinterpret_cast<uintptr_t>(a.big[j].src) | reinterpret_cast<uintptr_t>(a.big[j].dst)) % 16 == 0) &&
@@ -427,6 +514,7 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_minmax_kernel));
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_push_kernel<1>));
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_push_kernel<2>));
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, reinterpret_cast<const void*>(peer_push_bulk_kernel));
         if (e != cudaSuccess) rc = set_error(FDR_E_CUDA, "sync kernels: %s", cudaGetErrorString(e));
     }
     if (rc == FDR_OK) {  // flags and mailboxes start at zero (before any peer can have the handle)

@@ -68,10 +68,10 @@ def run_mode(half):
     back.set_row_ctas(0)
     drv.peer_sync = True
     drv.native = True
-    for lc in ((8, 16, 24, 32, 48, 64) if back.staged else (32,)):
+    for lc in ((2, 4, 8, 16, 32, 64) if back.staged else (32,)):
         back.set_link_ctas(lc)
         timed("native.link%d" % lc, True, True, 0)
-    back.set_link_ctas(32)
+    back.set_link_ctas(16)
     # per-phase times of the serial schedule
     ph = np.zeros(7)
     reps = 5
@@ -93,6 +93,24 @@ def run_mode(half):
     res["variants"]["%s.phases_ms" % tag] = dict(zip(["phase1", "exchange1", "phase2", "exchange3", "phase3", "phase4", "total_serial"], ph))
     if rank == 0:
         print(tag, "phases", ph, flush=True)
+    if back.staged:   # the link kernel alone: time per exchange (all units) against the number of CTAs
+        for lc in (2, 4, 8, 16, 32, 64):
+            back.set_link_ctas(lc)
+            tx = []
+            for which in (back.exchange1, back.exchange3):
+                which(sh)
+                torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(3):
+                    which(sh)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                tx.append(maxr(e0.elapsed_time(e1)) / 3)
+            res["variants"]["%s.exchange_ms.link%d" % (tag, lc)] = tx
+            if rank == 0:
+                print(tag, "exchange1/3 ms at", lc, "CTAs:", tx, flush=True)
+        back.set_link_ctas(16)
     # barrier cost
     for name, ps in (("peer", True), ("nccl", False)):
         drv.peer_sync = ps
