@@ -82,6 +82,7 @@ struct RowPassArgs {
     float2* hp_peers[FDR_MAX_PEERS];  // half planes by column owner: column k < n/2 of plane u, global row g at
                                       // hp_peers[k >> hp_shift] + u*hp_plane + (g << hp_shift) + (k & mask); one entry when unsharded
     int hp_shift;                // log2(columns of the half plane per owner)
+    int hp_local;                // every hp_peers entry is memory of this GPU (L2 prefetch allowed)
     long long hp_plane;          // elements per plane in a half-plane slab = rows_padded << hp_shift
     float2* nyq_peers[FDR_MAX_PEERS]; // Nyquist columns: plane u, global row g at nyq_peers[u % nyq_world] + u*nyq_plane + g
     int nyq_world;

@@ -361,10 +361,13 @@ template <int LOGN, int IN_MODE> __device__ __forceinline__ void row_prefetch_ne
     if constexpr (IN_MODE == ROW_IN_COMPLEX) {
         l2_prefetch_run(a.cin + (long long)pair * a.cplane + (long long)row * N, 8LL * N * nr);
     } else if constexpr (IN_MODE == ROW_IN_HALF) {
-        if (a.hp_shift == LOGN - 1) {   // one owner holds whole half rows
-            const float2* base = a.hp_peers[0] + (long long)pair * a.hp_plane + ((long long)(a.row0 + row) << a.hp_shift);
-            l2_prefetch_run(base, 4LL * N * nr);
-            l2_prefetch_run(base + ((long long)a.pair_dist << a.hp_shift), 4LL * N * nr);
+        if (a.hp_shift == LOGN - 1 || a.hp_local) {   // one owner holds whole half rows, or all owner blocks are local
+            const int owners = 1 << (LOGN - 1 - a.hp_shift);
+            for (int g = 0; g < owners; ++g) {
+                const float2* base = a.hp_peers[g] + (long long)pair * a.hp_plane + ((long long)(a.row0 + row) << a.hp_shift);
+                l2_prefetch_run(base, (8LL << a.hp_shift) * nr);
+                l2_prefetch_run(base + ((long long)a.pair_dist << a.hp_shift), (8LL << a.hp_shift) * nr);
+            }
         }
     } else if constexpr (IN_MODE == ROW_IN_PAIR_U8 || IN_MODE == ROW_IN_ROWS2_U8) {
         const bool rows2 = (IN_MODE == ROW_IN_ROWS2_U8);

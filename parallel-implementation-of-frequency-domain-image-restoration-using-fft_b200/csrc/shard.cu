@@ -73,7 +73,7 @@ struct fdr_shard {
     // peer synchronisation area at the tail of the slab allocation (so the slab's IPC handle covers it): barrier flags
     // [SYNC_SETS][FDR_MAX_PEERS] u32, then the extrema mailbox [2][FDR_MAX_PEERS][C][2] f32, then one status word
     // STAGED mode (half-plane mode on more than one rank; FDR_SHARD_STAGED=0 keeps the fused form): the row passes work on
-    // LOCAL full-width half planes [C][Rl][Cp/2] (+ Nyquist [C][Rl]) and a separate link kernel on a few SMs pushes the
+    // LOCAL staging planes [C][owner][Rl][Ch] (+ Nyquist [C][Rl]) and a separate link kernel on a few SMs pushes the
     // column blocks to / from the peers' slabs, so the NVLink-bound transfers run beside the HBM-bound passes of other units
     // instead of holding every SM (exchange1 / exchange3 below).  The staging planes live in the same allocation as the slab
     // because the peers store into them in exchange 3.
@@ -179,12 +179,16 @@ void fill_half_peers(const fdr_shard* s, RowPassArgs& r) {
     r.nyq_plane = s->Rp;
 }
 
-// staged mode: the row passes see ONE owner holding all Cp/2 columns of the local rows (row index = local row)
+// staged mode: the row passes see every column owner's block in LOCAL memory -- staging plane [unit][owner][Rl][Ch], row
+// index = local row -- except this rank's own block, which is its slab itself (rows row0.. of it): nothing is copied for it.
+// world * Rl = Rp, so both layouts share the unit stride Rp * Ch.
 void fill_half_staged(const fdr_shard* s, RowPassArgs& r) {
-    r.hp_peers[0] = s->slab.p + s->stage_off;
+    for (int g = 0; g < s->world; ++g)
+        r.hp_peers[g] = (g == s->rank) ? s->slab.p + (size_t)s->row0 * s->Ch : s->slab.p + s->stage_off + (size_t)g * s->Rl * s->Ch;
     r.nyq_peers[0] = s->slab.p + s->stage_nyq_off;
-    r.hp_shift = ilog2(s->Cp / 2);
-    r.hp_plane = (long long)s->Rl * (s->Cp / 2);
+    r.hp_shift = ilog2(s->Ch);
+    r.hp_plane = (long long)s->Rp * s->Ch;
+    r.hp_local = 1;
     r.nyq_world = 1;
     r.nyq_plane = s->Rl;
     r.row0 = 0;
@@ -200,7 +204,7 @@ struct PushJob {
 };
 struct PushArgs {
     PushJob big[FDR_MAX_PEERS];       // equal shapes, one per destination rank
-    int nbig, nbig_shift;             // nbig = 1 << nbig_shift (the world size, or 1)
+    int nbig;
     const float2* small_src[FDR_MAX_PEERS];   // contiguous runs (Nyquist vectors)
     float2* small_dst[FDR_MAX_PEERS];
     int small_n[FDR_MAX_PEERS];
@@ -230,8 +234,8 @@ template <int V> __global__ void __launch_bounds__(512) peer_push_kernel(PushArg
             const long long i = i0 + u * stride;
             jb[u] = -1;
             if (i < total) {
-                const int j = (int)(i & (a.nbig - 1));
-                const long long w = i >> a.nbig_shift;
+                const int j = (int)(i % a.nbig);
+                const long long w = i / a.nbig;
                 const long long row = w >> vshift, col = w & ((1LL << vshift) - 1);
                 jb[u] = j;
                 off[u] = row * a.big[j].dst_pitch + col * V;
@@ -253,7 +257,7 @@ __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 __global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int rows_per_item, int segs_per_row, unsigned seg_bytes,
-                                                             long long items_per_job) {
+                                                             long long items_per_job, int contig) {
     extern __shared__ __align__(128) unsigned char push_smem[];
     __shared__ unsigned long long bar[PUSH_STAGES];
     if (blockIdx.x == 0 && threadIdx.x >= 32) {
@@ -267,8 +271,8 @@ __global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int row
     const long long mine = (total > blockIdx.x) ? (total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto decode = [&](long long k, int& j, long long& row0, int& nrows, long long& c0) {
         const long long idx = blockIdx.x + k * gridDim.x;
-        j = (int)(idx & (a.nbig - 1));
-        const long long w = idx >> a.nbig_shift;
+        j = (int)(idx % a.nbig);
+        const long long w = idx / a.nbig;
         const long long rg = w / segs_per_row;
         c0 = (w - rg * segs_per_row) * (long long)(seg_bytes / 8);   // elements
         row0 = rg * rows_per_item;
@@ -281,6 +285,10 @@ __global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int row
         decode(k, j, row0, nrows, c0);
         const int st = (int)(k % PUSH_STAGES);
         mbar_expect_tx(&bar[st], (unsigned)nrows * seg_bytes);
+        if (contig) {   // rows adjacent on both sides: the item is one run
+            bulk_load_1d(push_smem + (size_t)st * PUSH_STAGE_BYTES, a.big[j].src + row0 * a.big[j].src_pitch, (unsigned)nrows * seg_bytes, &bar[st]);
+            return;
+        }
         for (int r = 0; r < nrows; ++r)
             bulk_load_1d(push_smem + (size_t)st * PUSH_STAGE_BYTES + (size_t)r * seg_bytes, a.big[j].src + (row0 + r) * a.big[j].src_pitch + c0,
                          seg_bytes, &bar[st]);
@@ -293,9 +301,12 @@ __global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int row
         int j, nrows;
         long long row0, c0;
         decode(k, j, row0, nrows, c0);
-        for (int r = 0; r < nrows; ++r)
-            bulk_store_1d(a.big[j].dst + (row0 + r) * a.big[j].dst_pitch + c0, push_smem + (size_t)st * PUSH_STAGE_BYTES + (size_t)r * seg_bytes,
-                          seg_bytes);
+        if (contig)
+            bulk_store_1d(a.big[j].dst + row0 * a.big[j].dst_pitch, push_smem + (size_t)st * PUSH_STAGE_BYTES, (unsigned)nrows * seg_bytes);
+        else
+            for (int r = 0; r < nrows; ++r)
+                bulk_store_1d(a.big[j].dst + (row0 + r) * a.big[j].dst_pitch + c0, push_smem + (size_t)st * PUSH_STAGE_BYTES + (size_t)r * seg_bytes,
+                              seg_bytes);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (k + PUSH_STAGES - 1 < mine) {
             // the buffer of item k-1 is loaded next: its stores must have finished reading shared memory
@@ -307,7 +318,6 @@ __global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int row
 }
 
 cudaError_t launch_push(PushArgs& a, int ctas, cudaStream_t st) {
-    a.nbig_shift = a.nbig > 0 ? ilog2(a.nbig) : 0;
     static const bool use_bulk = !(getenv("FDR_SHARD_BULK") && atoi(getenv("FDR_SHARD_BULK")) == 0);
     if (use_bulk && a.nbig > 0 && a.big[0].row_shift >= 1) {
         const long long row_bytes = 8LL << a.big[0].row_shift;
@@ -319,7 +329,9 @@ cudaError_t launch_push(PushArgs& a, int ctas, cudaStream_t st) {
             const unsigned seg_bytes = (unsigned)(row_bytes < PUSH_STAGE_BYTES ? row_bytes : PUSH_STAGE_BYTES);
             const int segs_per_row = (int)(row_bytes / seg_bytes);
             int rows_per_item = PUSH_STAGE_BYTES / (int)seg_bytes;
-            if (rows_per_item > 64) rows_per_item = 64;   // tiny rows (tests): bound the copies one thread issues per item
+            bool contig = segs_per_row == 1;
+            for (int j = 0; j < a.nbig && contig; ++j) contig = a.big[j].src_pitch == (1LL << a.big[0].row_shift) && a.big[j].dst_pitch == a.big[j].src_pitch;
+            if (!contig && rows_per_item > 64) rows_per_item = 64;   // tiny rows (tests): bound the copies one thread issues per item
             const long long items_per_job = (long long)((a.big[0].rows + rows_per_item - 1) / rows_per_item) * segs_per_row;
             const size_t smem = (size_t)PUSH_STAGES * PUSH_STAGE_BYTES;
             cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(peer_push_bulk_kernel), smem);
@@ -327,7 +339,7 @@ cudaError_t launch_push(PushArgs& a, int ctas, cudaStream_t st) {
             long long total = items_per_job * a.nbig;
             int grid = ctas;
             if (total < grid) grid = total > 0 ? (int)total : 1;
-            peer_push_bulk_kernel<<<grid, 128, smem, st>>>(a, rows_per_item, segs_per_row, seg_bytes, items_per_job);
+            peer_push_bulk_kernel<<<grid, 128, smem, st>>>(a, rows_per_item, segs_per_row, seg_bytes, items_per_job, contig ? 1 : 0);
             return cudaGetLastError();
         }
     }
@@ -491,7 +503,7 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
         s->staged = world > 1 && !(sg && atoi(sg) == 0);
         if (s->staged) {
             s->stage_off = (end + 31) & ~(size_t)31;
-            s->stage_nyq_off = s->stage_off + (size_t)channels * s->Rl * (Cp / 2);
+            s->stage_nyq_off = s->stage_off + (size_t)channels * Rp * s->Ch;   // [C][owner][Rl][Ch]
             end = s->stage_nyq_off + (size_t)channels * s->Rl;
         }
         const char* lc = getenv("FDR_SHARD_LINK_CTAS");
@@ -856,15 +868,14 @@ FDR_API int fdr_shard_exchange1(fdr_shard* s, int unit_first, int unit_count, vo
     FDR_TRY(check_pairs(s, unit_first, unit_count));
     FDR_CUDA(cudaSetDevice(s->device));
     if (s->rows_local == 0) return FDR_OK;
-    const int Ch2 = s->Cp / 2;
     for (int u = unit_first; u < unit_first + unit_count; ++u) {
         PushArgs a{};
-        for (int g = 0; g < s->world; ++g) {
-            const int d = (g + s->rank) % s->world;   // start with our own block: every rank begins on a different link
+        for (int g = 1; g < s->world; ++g) {
+            const int d = (g + s->rank) % s->world;   // every rank starts on a different link; our own block is already in place
             PushJob& j = a.big[a.nbig++];
-            j.src = s->slab.p + s->stage_off + (size_t)u * s->Rl * Ch2 + (size_t)d * s->Ch;
+            j.src = s->slab.p + s->stage_off + (size_t)u * s->Rp * s->Ch + (size_t)d * s->Rl * s->Ch;
             j.dst = s->peer_host[(size_t)d] + (size_t)u * s->Rp * s->Ch + (size_t)s->row0 * s->Ch;
-            j.src_pitch = Ch2;
+            j.src_pitch = s->Ch;
             j.dst_pitch = s->Ch;
             j.rows = s->rows_local;
             j.row_shift = ilog2(s->Ch);
@@ -886,18 +897,19 @@ FDR_API int fdr_shard_exchange3(fdr_shard* s, int unit_first, int unit_count, vo
     if (!s->have_peers) return set_error(FDR_E_STATE, "exchange before fdr_shard_set_peers");
     FDR_TRY(check_pairs(s, unit_first, unit_count));
     FDR_CUDA(cudaSetDevice(s->device));
-    const int Ch2 = s->Cp / 2;
     for (int u = unit_first; u < unit_first + unit_count; ++u) {
         PushArgs a{};
         for (int g = 0; g < s->world; ++g) {
             const int d = (g + s->rank) % s->world;
-            PushJob& j = a.big[a.nbig++];
-            j.src = s->slab.p + (size_t)u * s->Rp * s->Ch + (size_t)d * s->Rl * s->Ch;
-            j.dst = s->peer_host[(size_t)d] + s->stage_off + (size_t)u * s->Rl * Ch2 + (size_t)s->rank * s->Ch;
-            j.src_pitch = s->Ch;
-            j.dst_pitch = Ch2;
-            j.rows = s->Rl;
-            j.row_shift = ilog2(s->Ch);
+            if (g > 0) {   // (g == 0: our own rows of our own columns stay in the slab, where phase 3 reads them)
+                PushJob& j = a.big[a.nbig++];
+                j.src = s->slab.p + (size_t)u * s->Rp * s->Ch + (size_t)d * s->Rl * s->Ch;
+                j.dst = s->peer_host[(size_t)d] + s->stage_off + (size_t)u * s->Rp * s->Ch + (size_t)s->rank * s->Rl * s->Ch;
+                j.src_pitch = s->Ch;
+                j.dst_pitch = s->Ch;
+                j.rows = s->Rl;
+                j.row_shift = ilog2(s->Ch);
+            }
             if (u % s->world == s->rank) {   // the Nyquist column of this unit lives here
                 a.small_src[a.nsmall] = s->slab.p + s->nyq_off + (size_t)u * s->Rp + (size_t)d * s->Rl;
                 a.small_dst[a.nsmall] = s->peer_host[(size_t)d] + s->stage_nyq_off + (size_t)u * s->Rl;

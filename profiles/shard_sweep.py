@@ -60,15 +60,16 @@ def run_mode(half):
             print("%s.%s: %.3f ms" % (tag, name, ms), flush=True)
 
     drv.native = False
-    timed("serial.nccl", False, False, 0)
+    if os.environ.get("SWEEP_FULL"):
+        timed("serial.nccl", False, False, 0)
+        timed("pipe.nccl", False, True, 0)
+        for ctas in ((0,) if back.staged else (0, 74, 120)):
+            timed("pipe.peer.ctas%d" % ctas, True, True, ctas)
     timed("serial.peer", True, False, 0)
-    timed("pipe.nccl", False, True, 0)
-    for ctas in ((0,) if back.staged else (0, 74, 120)):
-        timed("pipe.peer.ctas%d" % ctas, True, True, ctas)
     back.set_row_ctas(0)
     drv.peer_sync = True
     drv.native = True
-    for lc in ((2, 4, 8, 16, 32, 64) if back.staged else (32,)):
+    for lc in ((4, 8, 12, 16, 24, 32) if back.staged else (32,)):
         back.set_link_ctas(lc)
         timed("native.link%d" % lc, True, True, 0)
     back.set_link_ctas(16)
@@ -94,7 +95,7 @@ def run_mode(half):
     if rank == 0:
         print(tag, "phases", ph, flush=True)
     if back.staged:   # the link kernel alone: time per exchange (all units) against the number of CTAs
-        for lc in (2, 4, 8, 16, 32, 64):
+        for lc in (4, 8, 16, 32):
             back.set_link_ctas(lc)
             tx = []
             for which in (back.exchange1, back.exchange3):
