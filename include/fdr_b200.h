@@ -215,11 +215,15 @@ int fdr_shard_set_minmax_negated(fdr_shard* shard, int enabled);
 int fdr_shard_exchange1(fdr_shard* shard, int unit_first, int unit_count, void* stream);
 int fdr_shard_exchange3(fdr_shard* shard, int unit_first, int unit_count, void* stream);
 int fdr_shard_staged(const fdr_shard* shard, int* enabled);
-int fdr_shard_set_link_ctas(fdr_shard* shard, int ctas);
+int fdr_shard_set_link_ctas(fdr_shard* shard, int ctas);   /* 0: move the blocks with the copy engines instead (FDR_SHARD_LINK=ce) */
 /* The whole restoration of this rank's rows in one call, pipelined over the units: passes on a compute stream, exchanges
  * and barriers on two high-priority streams, events in between; ordered after / before `stream`.  Collective: every rank
  * calls it.  Needs the peer-memory barriers below (no NCCL / MPI on the per-image path).  mpi.cpp:95-111. */
 int fdr_shard_restore_rows(fdr_shard* shard, const void* d_in_rows_u8, void* d_out_rows_u8, void* stream);
+/* Diagnostics (environment FDR_SHARD_TIMELINE=1 before the first fdr_shard_restore_rows): ms from the start of the last restore to
+ * the end of every step, ms[kind * units + u], kinds 0 phase 1, 1 exchange 1, 2 barrier, 3 phase 2, 4 exchange 3, 5 barrier,
+ * 6 phase 3; ms[7 * units] = end of phase 4.  Synchronises the device. */
+int fdr_shard_timeline(fdr_shard* shard, float* ms, int capacity, int* count);
 /* Cross-rank synchronisation through flags in peer memory (the slab allocation carries them, so fdr_shard_set_peers is all
  * the set-up they need).  They replace the synchronisation implied by MPI_Alltoallv (fft_mpi.cpp:170-279) and keep NCCL /
  * MPI out of the per-image path.  fdr_shard_barrier: stream-ordered barrier; every rank calls it with the same `set`

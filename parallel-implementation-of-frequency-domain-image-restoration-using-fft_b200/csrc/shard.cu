@@ -80,6 +80,7 @@ struct fdr_shard {
     bool staged = false;
     size_t stage_off = 0, stage_nyq_off = 0;   // element offsets inside the slab allocation
     int link_ctas = 16;
+    int link_mode = 0;          // 0: link kernel (bulk copies from link_ctas CTAs); 1: the device's copy engines (cudaMemcpyAsync per block)
     // native pipelined driver (fdr_shard_restore_rows): compute / link / barrier streams and the events between them
     cudaStream_t st_cmp = nullptr, st_link = nullptr, st_bar = nullptr;
     std::vector<cudaEvent_t> ev;               // [7 * units + 2]
@@ -317,6 +318,29 @@ __global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int row
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the kernel (and the barrier after it) ends
 }
 
+// The same jobs on the copy engines: no SM, register or shared-memory footprint at all, so the passes of the other units keep
+// the whole GPU (the link kernel's CTAs each take an SM away from kernels that need all of its registers).
+cudaError_t push_copy_engine(const PushArgs& a, cudaStream_t st) {
+    for (int j = 0; j < a.nbig; ++j) {
+        const PushJob& b = a.big[j];
+        if (b.rows <= 0) continue;
+        const size_t row_bytes = sizeof(float2) << b.row_shift;
+        cudaError_t e;
+        if (b.src_pitch == (1LL << b.row_shift) && b.dst_pitch == b.src_pitch)
+            e = cudaMemcpyAsync(b.dst, b.src, row_bytes * b.rows, cudaMemcpyDeviceToDevice, st);
+        else
+            e = cudaMemcpy2DAsync(b.dst, (size_t)b.dst_pitch * sizeof(float2), b.src, (size_t)b.src_pitch * sizeof(float2), row_bytes, b.rows,
+                                  cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    for (int j = 0; j < a.nsmall; ++j) {
+        if (a.small_n[j] <= 0) continue;
+        cudaError_t e = cudaMemcpyAsync(a.small_dst[j], a.small_src[j], sizeof(float2) * a.small_n[j], cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_push(PushArgs& a, int ctas, cudaStream_t st) {
     static const bool use_bulk = !(getenv("FDR_SHARD_BULK") && atoi(getenv("FDR_SHARD_BULK")) == 0);
     if (use_bulk && a.nbig > 0 && a.big[0].row_shift >= 1) {
@@ -506,6 +530,8 @@ FDR_API int fdr_shard_create(fdr_shard** out, int rows, int cols, int channels, 
             s->stage_nyq_off = s->stage_off + (size_t)channels * Rp * s->Ch;   // [C][owner][Rl][Ch]
             end = s->stage_nyq_off + (size_t)channels * s->Rl;
         }
+        const char* lm = getenv("FDR_SHARD_LINK");   // "ce": copy engines, "bulk": link kernel
+        if (lm) s->link_mode = (lm[0] == 'c') ? 1 : 0;
         const char* lc = getenv("FDR_SHARD_LINK_CTAS");
         if (lc && atoi(lc) > 0) s->link_ctas = atoi(lc);
         s->sync_off = (end + 31) & ~(size_t)31;
@@ -885,7 +911,10 @@ FDR_API int fdr_shard_exchange1(fdr_shard* s, int unit_first, int unit_count, vo
         a.small_dst[0] = s->peer_host[(size_t)owner] + s->nyq_off + (size_t)u * s->Rp + s->row0;
         a.small_n[0] = s->rows_local;
         a.nsmall = 1;
-        FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
+        if (s->link_mode == 1)
+            FDR_CUDA(push_copy_engine(a, pick(s, stream)));
+        else
+            FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
         s->launches += 1;
     }
     return FDR_OK;
@@ -917,7 +946,10 @@ FDR_API int fdr_shard_exchange3(fdr_shard* s, int unit_first, int unit_count, vo
                 a.nsmall++;
             }
         }
-        FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
+        if (s->link_mode == 1)
+            FDR_CUDA(push_copy_engine(a, pick(s, stream)));
+        else
+            FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
         s->launches += 1;
     }
     return FDR_OK;
@@ -930,8 +962,13 @@ FDR_API int fdr_shard_staged(const fdr_shard* s, int* enabled) {
 }
 
 FDR_API int fdr_shard_set_link_ctas(fdr_shard* s, int ctas) {
-    if (!s || ctas < 1) return set_error(FDR_E_INVALID, "bad arguments");
-    s->link_ctas = ctas;
+    if (!s || ctas < 0) return set_error(FDR_E_INVALID, "bad arguments");
+    if (ctas == 0) {   // 0 selects the copy engines
+        s->link_mode = 1;
+    } else {
+        s->link_mode = 0;
+        s->link_ctas = ctas;
+    }
     return FDR_OK;
 }
 
@@ -952,7 +989,8 @@ FDR_API int fdr_shard_restore_rows(fdr_shard* s, const void* d_in_rows_u8, void*
         FDR_CUDA(cudaStreamCreateWithPriority(&s->st_link, cudaStreamNonBlocking, hi));
         FDR_CUDA(cudaStreamCreateWithPriority(&s->st_bar, cudaStreamNonBlocking, hi));
         s->ev.resize((size_t)7 * U + 2);
-        for (auto& e : s->ev) FDR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const bool timeline = getenv("FDR_SHARD_TIMELINE") && atoi(getenv("FDR_SHARD_TIMELINE")) != 0;   // timing events: fdr_shard_timeline
+        for (auto& e : s->ev) FDR_CUDA(cudaEventCreateWithFlags(&e, timeline ? cudaEventDefault : cudaEventDisableTiming));
     }
     cudaStream_t caller = pick(s, stream);
     auto E = [&](int kind, int u) { return s->ev[(size_t)kind * U + u]; };   // kinds 0..6
@@ -1002,11 +1040,36 @@ FDR_API int fdr_shard_restore_rows(fdr_shard* s, const void* d_in_rows_u8, void*
     for (int u = 0; u < U; ++u) {   // rows inverse
         if (!one) FDR_CUDA(cudaStreamWaitEvent(s->st_cmp, E(5, u), 0));
         FDR_TRY(fdr_shard_phase3_pairs(s, u, 1, s->st_cmp));
+        FDR_CUDA(cudaEventRecord(E(6, u), s->st_cmp));
     }
     if (!one) FDR_TRY(fdr_shard_minmax_allreduce(s, s->st_cmp));
     FDR_TRY(fdr_shard_phase4_pack(s, d_out_rows_u8, s->st_cmp));
     FDR_CUDA(cudaEventRecord(ev_join, s->st_cmp));
     FDR_CUDA(cudaStreamWaitEvent(caller, ev_join, 0));
+    return FDR_OK;
+}
+
+// Diagnostics (FDR_SHARD_TIMELINE=1 at the first fdr_shard_restore_rows): milliseconds from the start of the last restore to
+// the END of every step, ms[kind * units + u] with kind 0 phase 1, 1 exchange 1, 2 barrier, 3 phase 2, 4 exchange 3, 5 barrier,
+// 6 phase 3, and ms[7 * units] = the end of phase 4.  Synchronises the device.  Entries of skipped steps are negative.
+FDR_API int fdr_shard_timeline(fdr_shard* s, float* ms, int capacity, int* count) {
+    if (!s || !ms || !count) return set_error(FDR_E_INVALID, "bad arguments");
+    if (s->ev.empty()) return set_error(FDR_E_STATE, "no restore has run");
+    FDR_CUDA(cudaSetDevice(s->device));
+    FDR_CUDA(cudaDeviceSynchronize());
+    const int U = s->units, n = 7 * U + 1;
+    if (capacity < n) return set_error(FDR_E_INVALID, "need room for %d values", n);
+    cudaEvent_t t0 = s->ev[(size_t)7 * U];
+    for (int i = 0; i < n; ++i) {
+        cudaEvent_t e = (i < 7 * U) ? s->ev[(size_t)i] : s->ev[(size_t)7 * U + 1];
+        float v = -1.f;
+        if (cudaEventElapsedTime(&v, t0, e) != cudaSuccess) {
+            v = -1.f;
+            cudaGetLastError();
+        }
+        ms[i] = v;
+    }
+    *count = n;
     return FDR_OK;
 }
 

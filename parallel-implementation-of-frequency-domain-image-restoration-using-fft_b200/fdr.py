@@ -105,6 +105,7 @@ def lib():
             "fdr_shard_staged": [vp, C.POINTER(i)],
             "fdr_shard_set_link_ctas": [vp, i],
             "fdr_shard_restore_rows": [vp, vp, vp, vp],
+            "fdr_shard_timeline": [vp, _fp, i, C.POINTER(i)],
             "fdr_shard_barrier": [vp, i, vp],
             "fdr_shard_minmax_allreduce": [vp, vp],
             "fdr_shard_sync_status": [vp, vp, C.POINTER(i)],
@@ -382,6 +383,17 @@ class Shard:
 
     def restore_rows_native(self, d_in_rows, d_out_rows, stream=0):
         _check(lib().fdr_shard_restore_rows(self.h, d_in_rows, d_out_rows, stream))
+
+    def timeline(self):
+        """FDR_SHARD_TIMELINE=1: {step: [ms from the start of the last native restore to the end of the step, per unit]}."""
+        buf = np.zeros(128, np.float32)
+        n = C.c_int(0)
+        _check(lib().fdr_shard_timeline(self.h, _p(buf), 128, C.byref(n)))
+        U = (n.value - 1) // 7
+        names = ["phase1", "exchange1", "barrier1", "phase2", "exchange3", "barrier3", "phase3"]
+        out = {nm: [round(float(x), 4) for x in buf[k * U:(k + 1) * U]] for k, nm in enumerate(names)}
+        out["phase4"] = round(float(buf[7 * U]), 4)
+        return out
 
     def peer_barrier(self, set_index, stream=0):
         _check(lib().fdr_shard_barrier(self.h, int(set_index), stream))

@@ -69,7 +69,7 @@ def run_mode(half):
     back.set_row_ctas(0)
     drv.peer_sync = True
     drv.native = True
-    for lc in ((4, 8, 12, 16, 24, 32) if back.staged else (32,)):
+    for lc in ((0, 8, 16, 24, 32) if back.staged else (32,)):
         back.set_link_ctas(lc)
         timed("native.link%d" % lc, True, True, 0)
     back.set_link_ctas(16)
@@ -95,7 +95,7 @@ def run_mode(half):
     if rank == 0:
         print(tag, "phases", ph, flush=True)
     if back.staged:   # the link kernel alone: time per exchange (all units) against the number of CTAs
-        for lc in (4, 8, 16, 32):
+        for lc in (0, 8, 16, 32):
             back.set_link_ctas(lc)
             tx = []
             for which in (back.exchange1, back.exchange3):

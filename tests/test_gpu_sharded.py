@@ -46,7 +46,8 @@ def single_gpu(gpu, img, psf_len, psf_ang, half):
             os.environ["FDR_HALF"] = old
 
 
-def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang, half=False, row_ctas=0, negated=False, staged=True, native=False):
+def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang, half=False, row_ctas=0, negated=False, staged=True, native=False,
+                 link_ctas=None):
     H, W, C = images_hwc.shape
     dev = torch.device("cuda", 0)
     d_in = torch.from_numpy(images_hwc).to(dev)
@@ -61,6 +62,8 @@ def run_emulated(gpu, torch, images_hwc, world, psf_len, psf_ang, half=False, ro
             s.set_psf_motion(psf_len, psf_ang, K)
             if row_ctas:
                 s.set_row_ctas(row_ctas)
+            if link_ctas is not None:
+                s.set_link_ctas(link_ctas)   # 0 = copy engines, n = link kernel on n CTAs
             if negated:
                 s.set_minmax_negated(True)
         half_on = shards[0].half_plane
@@ -284,10 +287,16 @@ def test_sharded_staged_equals_fused_and_native_driver(gpu, oracle, H, W, world,
     fused, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=False)
     staged, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=True)
     assert np.array_equal(staged, fused), u8_gate(staged, fused)
-    for st in (True, False):
-        native, launches = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=st, native=True, negated=True)
+    # (the copy-engine link is not driven natively here: with all shards on ONE device their copies share the engines' in-order
+    # queues, and a copy waiting on another shard's barrier would block the copy that barrier waits for; it runs serially below)
+    for st, link in ((True, None), (True, 3), (False, None)):
+        native, launches = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=st, native=True, negated=True, link_ctas=link)
         assert launches > 0
-        assert np.array_equal(native, fused), (st, u8_gate(native, fused))
-    pair_native, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=False, native=True)
+        assert np.array_equal(native, fused), (st, link, u8_gate(native, fused))
+    ce, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=True, staged=True, link_ctas=0)
+    assert np.array_equal(ce, fused)
+    # serial first: it loads the plane-pair kernels (a lazily loaded kernel cannot be loaded while another shard of this
+    # process spins in a barrier -- only a concern with several shards in one process on one device)
     pair, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=False)
+    pair_native, _ = run_emulated(gpu, torch, img, world, 9, 30.0, half=False, native=True)
     assert np.array_equal(pair_native, pair)
