@@ -215,6 +215,7 @@ int fdr_shard_set_minmax_negated(fdr_shard* shard, int enabled);
 int fdr_shard_exchange1(fdr_shard* shard, int unit_first, int unit_count, void* stream);
 int fdr_shard_exchange3(fdr_shard* shard, int unit_first, int unit_count, void* stream);
 int fdr_shard_staged(const fdr_shard* shard, int* enabled);
+int fdr_shard_set_ce_streams(fdr_shard* shard, int streams);   /* copy-engine mode: blocks of an exchange spread over 1..8 streams */
 int fdr_shard_set_link_ctas(fdr_shard* shard, int ctas);   /* 0: move the blocks with the copy engines instead (FDR_SHARD_LINK=ce) */
 /* The whole restoration of this rank's rows in one call, pipelined over the units: passes on a compute stream, exchanges
  * and barriers on two high-priority streams, events in between; ordered after / before `stream`.  Collective: every rank

@@ -123,6 +123,8 @@ cudaError_t launch_row_pass(const RowPassArgs& a, cudaStream_t s);
 cudaError_t launch_col_pass(const ColPassArgs& a, cudaStream_t s);
 // Twiddle table for power-of-two length n on the current device (cached).
 cudaError_t get_twiddles(int n, const float2** out);
+// table of the 32-points-per-thread long-row core (fft_mid.cuh), n = 8192 or 16384
+cudaError_t get_twiddles_mid(int n, const float2** out);
 // Long columns (n = 8192, 16384), COL_WIENER / COL_MAKE_WIENER: split column pass -- K x 2048 blocks (col_blocks.cu) when the
 // wide TMA kernel applies, else 128 x 128 four-step (col_split.cuh).  The Wiener factor it reads/writes is in digit-swapped row
 // order: row M*k1 + k2 holds frequency k1 + (n/M)*k2 with M = col_split_block_len(args) (2048 or 128).

@@ -3,6 +3,7 @@
 #include <mutex>
 #include <utility>
 
+#include "fft_mid.cuh"
 #include "passes.h"
 
 namespace fdr {
@@ -112,6 +113,39 @@ cudaError_t get_twiddles(int n, const float2** out) {
         return e;
     }
     cache[{dev, l}] = p;
+    *out = p;
+    return cudaSuccess;
+}
+
+cudaError_t get_twiddles_mid(int n, const float2** out) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, float2*> cache;
+    *out = nullptr;
+    if (n != 8192 && n != 16384) return cudaErrorInvalidValue;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, n});
+    if (it != cache.end()) {
+        *out = it->second;
+        return cudaSuccess;
+    }
+    const int total = (n == 16384) ? MidGeom<16384>::TW_ENTRIES : MidGeom<8192>::TW_ENTRIES;
+    float2* p = nullptr;
+    e = cudaMalloc(&p, sizeof(float2) * (size_t)total);
+    if (e != cudaSuccess) return e;
+    if (n == 16384)
+        mid_tw_fill_kernel<16384><<<(total + 255) / 256, 256>>>(p);
+    else
+        mid_tw_fill_kernel<8192><<<(total + 255) / 256, 256>>>(p);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return e;
+    }
+    cache[{dev, n}] = p;
     *out = p;
     return cudaSuccess;
 }

@@ -3,6 +3,7 @@
 // compile in parallel.
 #pragma once
 #include "fft_core.cuh"
+#include "fft_mid.cuh"
 #include "passes.h"
 
 namespace fdr {
@@ -25,16 +26,24 @@ __device__ __forceinline__ unsigned int f32_ordered(float f) {
 // ---------------------------------------------------------------------------------
 template <int LOGN> struct RowGeom {
     static constexpr int N = 1 << LOGN;
-    static constexpr int E = FftGeom<N>::E;
-    static constexpr int T = FftGeom<N>::T;
+    static constexpr bool MID = (LOGN >= 13);  // long rows: 32 points per thread (fft_mid.cuh)
+    static constexpr int E = MID ? 32 : FftGeom<N>::E;
+    static constexpr int T = N / E;
     static constexpr int RPC = (T >= 128) ? 1 : (128 / T);
     static constexpr int THREADS = T * RPC;
-    static constexpr int MIN_BLOCKS = (THREADS == 128 && N >= 1024) ? 9 : 1;
+    static constexpr int MIN_BLOCKS = MID ? (LOGN == 13 ? 2 : 1) : ((THREADS == 128 && N >= 1024) ? 9 : 1);
     // double-buffered exchange (one barrier per exchange) while two buffers of all rows fit 32 KB
     static constexpr bool DB = false;  // measured slower on B200: the second buffer costs one resident CTA per SM
-    static constexpr int EXW = ex_words<N, 1>();  // float2 words of one row's exchange buffer
-    static constexpr size_t SMEM = fft_smem_bytes<N, 1>() * RPC * (DB ? 2 : 1);
+    static constexpr int EXW = MID ? mid_skew(N) : ex_words<N, 1>();  // float2 words of one row's exchange buffer
+    static constexpr size_t SMEM = MID ? (size_t)EXW * sizeof(float2) : fft_smem_bytes<N, 1>() * RPC * (DB ? 2 : 1);
 };
+// the row transform of the geometry above
+template <int LOGN> __device__ __forceinline__ void row_fft(float2* v, float2* ex, const float2* __restrict__ tw, int t) {
+    if constexpr (RowGeom<LOGN>::MID)
+        fft_mid_forward<(1 << LOGN)>(v, ex, tw, t);
+    else
+        fft_forward<(1 << LOGN), 1, RowGeom<LOGN>::DB>(v, ex, tw, t, 0);
+}
 
 // One block of RPC rows of pair (half-plane forms: plane) blockIdx.y; `row_block` is blockIdx.x in the one-shot kernel
 // and the loop index in the persistent one.
@@ -44,7 +53,7 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
     constexpr int N = Gm::N, E = Gm::E, T = Gm::T, RPC = Gm::RPC;
     constexpr bool IN_ROWS2 = (IN_MODE == ROW_IN_ROWS2_F32 || IN_MODE == ROW_IN_ROWS2_U8);
     constexpr bool HALF = IN_ROWS2 || IN_MODE == ROW_IN_HALF || OUT_MODE == ROW_OUT_HALF || OUT_MODE == ROW_OUT_REAL_ROWS2;
-    static_assert(!HALF || (E == 16 && N >= FDR_HALF_MIN_N), "half-plane forms need 16 points per thread");
+    static_assert(!HALF || (E >= 16 && N >= FDR_HALF_MIN_N), "half-plane forms need at least 16 points per thread");
     constexpr int H8 = E / 2;  // points of the lower half spectrum per thread
     extern __shared__ float2 smem2[];
     const int tid = threadIdx.x;
@@ -197,7 +206,7 @@ __device__ __forceinline__ void row_pass_body(const RowPassArgs& a, const int ro
         }
     }
 
-    fft_forward<N, 1, Gm::DB>(v, ex, a.tw, t, 0);
+    row_fft<LOGN>(v, ex, a.tw, t);
 
     if constexpr (OUT_MODE == ROW_OUT_HALF) {
         // Untangle Z = FFT(row_y + i row_{y+D}): thread t needs Z[N - k] for its k = t + T*m (m < 8), held by thread T - t
@@ -492,8 +501,17 @@ __global__ void __launch_bounds__(ColGeom<LOGN, CW>::THREADS, (ColGeom<LOGN, CW>
     }
 }
 
-template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row_variant(const RowPassArgs& a, cudaStream_t s) {
+template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row_variant(const RowPassArgs& a0, cudaStream_t s) {
     using Gm = RowGeom<LOGN>;
+    RowPassArgs a = a0;
+    if constexpr (LOGN >= 13) {
+        static const int pf = getenv("FDR_ROW_PREFETCH") ? atoi(getenv("FDR_ROW_PREFETCH")) : -1;   // row blocks ahead; 0 = off
+        a.prefetch_dist = pf >= 0 ? pf : device_sm_count() * Gm::MIN_BLOCKS;
+    }
+    if constexpr (Gm::MID) {   // the long-row core has its own twiddle table (the caller's is the 16-point core's)
+        cudaError_t e = get_twiddles_mid(1 << LOGN, &a.tw);
+        if (e != cudaSuccess) return e;
+    }
     if (Gm::SMEM > 48 * 1024) {
         cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ>), Gm::SMEM);
         if (e != cudaSuccess) return e;
@@ -506,16 +524,10 @@ template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ> cudaError_t launch_row
                 if (e != cudaSuccess) return e;
             }
             grid.x = a.max_ctas;
+            a.prefetch_dist = 0;
             row_pass_persist_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
             return cudaGetLastError();
         }
-    }
-    if constexpr (LOGN >= 13) {
-        static const int pf = getenv("FDR_ROW_PREFETCH") ? atoi(getenv("FDR_ROW_PREFETCH")) : -1;   // row blocks ahead; 0 = off
-        RowPassArgs b = a;
-        b.prefetch_dist = pf >= 0 ? pf : device_sm_count() * (LOGN == 14 ? 1 : 2);
-        row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(b);
-        return cudaGetLastError();
     }
     row_pass_kernel<LOGN, IN_MODE, OUT_MODE, CONJ><<<grid, Gm::THREADS, Gm::SMEM, s>>>(a);
     return cudaGetLastError();

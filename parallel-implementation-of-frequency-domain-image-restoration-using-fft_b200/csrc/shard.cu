@@ -81,6 +81,9 @@ struct fdr_shard {
     size_t stage_off = 0, stage_nyq_off = 0;   // element offsets inside the slab allocation
     int link_ctas = 16;
     int link_mode = 0;          // 0: link kernel (bulk copies from link_ctas CTAs); 1: the device's copy engines (cudaMemcpyAsync per block)
+    int ce_streams = 4;         // copy-engine mode: the blocks of one exchange are spread over this many streams (engines)
+    cudaStream_t st_ce[8] = {};
+    cudaEvent_t ev_ce[9] = {};
     // native pipelined driver (fdr_shard_restore_rows): compute / link / barrier streams and the events between them
     cudaStream_t st_cmp = nullptr, st_link = nullptr, st_bar = nullptr;
     std::vector<cudaEvent_t> ev;               // [7 * units + 2]
@@ -320,25 +323,49 @@ __global__ void __launch_bounds__(128) peer_push_bulk_kernel(PushArgs a, int row
 
 // The same jobs on the copy engines: no SM, register or shared-memory footprint at all, so the passes of the other units keep
 // the whole GPU (the link kernel's CTAs each take an SM away from kernels that need all of its registers).
-cudaError_t push_copy_engine(const PushArgs& a, cudaStream_t st) {
+cudaError_t push_copy_engine(fdr_shard* s, const PushArgs& a, cudaStream_t st) {
+    // one stream keeps one engine busy (~360 GB/s measured over NVLink); the blocks go round-robin over `ce_streams` side
+    // streams forked from and joined back into `st`, so the exchange still looks like one stream-ordered operation
+    const int NL = s->ce_streams < 1 ? 1 : (s->ce_streams > 8 ? 8 : s->ce_streams);
+    cudaError_t e = cudaSuccess;
+    if (NL > 1) {
+        if (!s->st_ce[0]) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&s->st_ce[i], cudaStreamNonBlocking, hi);
+            for (int i = 0; i < 9 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&s->ev_ce[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        e = cudaEventRecord(s->ev_ce[8], st);
+        for (int i = 0; i < NL && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(s->st_ce[i], s->ev_ce[8], 0);
+        if (e != cudaSuccess) return e;
+    }
+    int k = 0;
     for (int j = 0; j < a.nbig; ++j) {
         const PushJob& b = a.big[j];
         if (b.rows <= 0) continue;
+        cudaStream_t q = NL > 1 ? s->st_ce[k++ % NL] : st;
         const size_t row_bytes = sizeof(float2) << b.row_shift;
-        cudaError_t e;
         if (b.src_pitch == (1LL << b.row_shift) && b.dst_pitch == b.src_pitch)
-            e = cudaMemcpyAsync(b.dst, b.src, row_bytes * b.rows, cudaMemcpyDeviceToDevice, st);
+            e = cudaMemcpyAsync(b.dst, b.src, row_bytes * b.rows, cudaMemcpyDeviceToDevice, q);
         else
             e = cudaMemcpy2DAsync(b.dst, (size_t)b.dst_pitch * sizeof(float2), b.src, (size_t)b.src_pitch * sizeof(float2), row_bytes, b.rows,
-                                  cudaMemcpyDeviceToDevice, st);
+                                  cudaMemcpyDeviceToDevice, q);
         if (e != cudaSuccess) return e;
     }
     for (int j = 0; j < a.nsmall; ++j) {
         if (a.small_n[j] <= 0) continue;
-        cudaError_t e = cudaMemcpyAsync(a.small_dst[j], a.small_src[j], sizeof(float2) * a.small_n[j], cudaMemcpyDeviceToDevice, st);
+        cudaStream_t q = NL > 1 ? s->st_ce[k++ % NL] : st;
+        e = cudaMemcpyAsync(a.small_dst[j], a.small_src[j], sizeof(float2) * a.small_n[j], cudaMemcpyDeviceToDevice, q);
         if (e != cudaSuccess) return e;
     }
-    return cudaSuccess;
+    if (NL > 1) {
+        for (int i = 0; i < NL && e == cudaSuccess; ++i) {
+            e = cudaEventRecord(s->ev_ce[i], s->st_ce[i]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, s->ev_ce[i], 0);
+        }
+    }
+    return e;
 }
 
 cudaError_t launch_push(PushArgs& a, int ctas, cudaStream_t st) {
@@ -595,6 +622,10 @@ FDR_API int fdr_shard_destroy(fdr_shard* s) {
     s->self_only.release();
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : s->ev_ce)
+        if (e) cudaEventDestroy(e);
+    for (auto& q : s->st_ce)
+        if (q) cudaStreamDestroy(q);
     if (s->st_cmp) cudaStreamDestroy(s->st_cmp);
     if (s->st_link) cudaStreamDestroy(s->st_link);
     if (s->st_bar) cudaStreamDestroy(s->st_bar);
@@ -912,7 +943,7 @@ FDR_API int fdr_shard_exchange1(fdr_shard* s, int unit_first, int unit_count, vo
         a.small_n[0] = s->rows_local;
         a.nsmall = 1;
         if (s->link_mode == 1)
-            FDR_CUDA(push_copy_engine(a, pick(s, stream)));
+            FDR_CUDA(push_copy_engine(s, a, pick(s, stream)));
         else
             FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
         s->launches += 1;
@@ -947,11 +978,17 @@ FDR_API int fdr_shard_exchange3(fdr_shard* s, int unit_first, int unit_count, vo
             }
         }
         if (s->link_mode == 1)
-            FDR_CUDA(push_copy_engine(a, pick(s, stream)));
+            FDR_CUDA(push_copy_engine(s, a, pick(s, stream)));
         else
             FDR_CUDA(launch_push(a, s->link_ctas, pick(s, stream)));
         s->launches += 1;
     }
+    return FDR_OK;
+}
+
+FDR_API int fdr_shard_set_ce_streams(fdr_shard* s, int streams) {
+    if (!s || streams < 1 || streams > 8) return set_error(FDR_E_INVALID, "1..8 copy streams");
+    s->ce_streams = streams;
     return FDR_OK;
 }
 

@@ -104,6 +104,7 @@ def lib():
             "fdr_shard_exchange3": [vp, i, i, vp],
             "fdr_shard_staged": [vp, C.POINTER(i)],
             "fdr_shard_set_link_ctas": [vp, i],
+            "fdr_shard_set_ce_streams": [vp, i],
             "fdr_shard_restore_rows": [vp, vp, vp, vp],
             "fdr_shard_timeline": [vp, _fp, i, C.POINTER(i)],
             "fdr_shard_barrier": [vp, i, vp],
@@ -372,6 +373,9 @@ class Shard:
 
     def set_link_ctas(self, n):
         _check(lib().fdr_shard_set_link_ctas(self.h, int(n)))
+
+    def set_ce_streams(self, n):
+        _check(lib().fdr_shard_set_ce_streams(self.h, int(n)))
 
     def exchange1(self, stream=0, pair=None):
         first, count = (0, self.npairs) if pair is None else (pair, 1)

@@ -22,8 +22,31 @@ d_in = torch.empty((max(back.n_rows, 1), W, 3), dtype=torch.uint8, device=dev)
 d_out = torch.zeros_like(d_in)
 fdr.synth_rows_device_u8(d_in.data_ptr(), 0xF17E0004, 0, 3, H, W, back.first_row, back.n_rows, sh)
 torch.cuda.synchronize()
-for lc in [int(x) for x in sys.argv[1:]] or [0, 32]:
-    back.set_link_ctas(lc)
+def maxr(x):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+for arg in sys.argv[1:] or ["ce4", "32"]:   # "ceN": copy engines over N streams; "N": link kernel on N CTAs
+    if arg.startswith("ce"):
+        lc = 0
+        back.set_link_ctas(0)
+        back.set_ce_streams(int(arg[2:] or 4))
+    else:
+        lc = int(arg)
+        back.set_link_ctas(lc)
+    tx = []
+    for which in (back.exchange1, back.exchange3):   # the exchange alone, all units
+        which(sh)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(3):
+            which(sh)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        tx.append(round(maxr(a0.elapsed_time(a1)) / 3, 4))
     for _ in range(5):
         drv.restore_rows(d_in.data_ptr(), d_out.data_ptr(), sh)
     torch.cuda.synchronize()
@@ -37,7 +60,7 @@ for lc in [int(x) for x in sys.argv[1:]] or [0, 32]:
     torch.cuda.synchronize()
     tl = back.timeline()
     if rank == 0:
-        print("link_ctas", lc, "ms/step %.3f" % (e0.elapsed_time(e1) / 10), json.dumps(tl), flush=True)
+        print("link", arg, "exchange1/3 alone ms", tx, "ms/step %.3f" % (e0.elapsed_time(e1) / 10), json.dumps(tl), flush=True)
     dist.barrier()
 back.close()
 dist.destroy_process_group()
