@@ -209,7 +209,7 @@ int fdr_shard_set_minmax_negated(fdr_shard* shard, int enabled);
 /* STAGED mode (the default in half-plane mode on more than one rank; FDR_SHARD_STAGED=0 keeps the fused stores/loads): phase 1
  * and phase 3 work on LOCAL staging planes and these two calls move the column blocks between the ranks -- exchange 1 after
  * phase 1 (row spectra -> the column owners' slabs), exchange 3 after phase 2 (filtered columns -> the row owners' staging
- * planes) -- as plain stores over NVLink from a few persistent CTAs (fdr_shard_set_link_ctas, default 16), so a transfer
+ * planes) -- as plain stores over NVLink from a few persistent CTAs (fdr_shard_set_link_ctas, default 24), so a transfer
  * runs beside the passes of other units instead of holding every SM.  A barrier must follow each exchange.  No-ops when the
  * shard is not staged.  They are the MPI_Alltoallv calls of fft_mpi.cpp:284-307. */
 int fdr_shard_exchange1(fdr_shard* shard, int unit_first, int unit_count, void* stream);

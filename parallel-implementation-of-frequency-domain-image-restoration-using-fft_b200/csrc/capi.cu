@@ -248,7 +248,7 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
         float2* const ss_l = p->ss.p + (size_t)lane * p->ws_units;
         float* const mmf_l = p->mmf.p + (size_t)lane * p->ws_units * 2;
         p->last_lane = lane;
-        FDR_CUDA(launch_minmax_reset(mm_l, nu, s));
+        // the slots are re-armed by CTA 0 of every pair in pass 1 (RowPassArgs::mm_reset): no separate launch
         // An odd plane count leaves one plane without a partner: it takes the half-plane path (passes.h) on a side stream,
         // beside the pairs, instead of travelling as a half-empty complex pair.
         const bool lone = (nu & 1) && p->half_ok;
@@ -280,6 +280,8 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
             r1.cout = spec_l;
             r1.cplane = (long long)p->plane_elems();
             r1.tw = p->tw_rows;
+            r1.mm_reset = mm_l;
+            r1.local_units = nu;
             {
                 KernelTimer kt(p, s, 0, px_in1 * (lone ? nu - 1 : nu) + 8.0 * p->H * p->Cp * npf);
                 FDR_CUDA(launch_row_pass(r1, s));
@@ -353,6 +355,8 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
             h1.unit_base = base;
             h1.units_total = n_units;
             h1.tw = p->tw_rows;
+            h1.mm_reset = mm_l;
+            h1.local_units = nu;
             h1.pair_dist = D1;
             h1.rows_in = p->H;
             h1.hp_rows_store = p->H;
@@ -429,9 +433,18 @@ int restore_units_device(fdr_plan* p, const InputDesc& in, float* out_f32, uint8
             }
         }
 
-        FDR_CUDA(launch_minmax_finalize(mm_l, ss_l, mmf_l, nu, s));
-        p->launches += 2;
-        if (out_u8 && p->white_balance && C == 3) {
+        // a chunk of one or two BGR images: the pack folds the slots itself (one launch less on the launch-bound small images)
+        const bool fused_pack = out_u8 && !out_f32 && !(p->white_balance && C == 3) &&
+                                pack_u8_c3_fused_applicable(raw_l, HW, out_u8 + base * HW, nu / C, C, p->H, p->W);
+        if (!fused_pack) {
+            FDR_CUDA(launch_minmax_finalize(mm_l, ss_l, mmf_l, nu, s));
+            p->launches += 1;
+        }
+        if (fused_pack) {
+            KernelTimer kt(p, s, 3, 5.0 * HW * nu);
+            FDR_CUDA(launch_pack_u8_c3_fused(raw_l, HW, mm_l, ss_l, mmf_l, out_u8 + base * HW, nu / C, p->H, p->W, s));
+            p->launches += 1;
+        } else if (out_u8 && p->white_balance && C == 3) {
             KernelTimer kt(p, s, 3, (2 * 12.0 + 3.0 + (in.mode == ROW_IN_PAIR_U8 ? 3.0 : 12.0)) * HW * (nu / 3));
             const uint8_t* o8 = in.mode == ROW_IN_PAIR_U8 ? in.u8 + base * HW : nullptr;
             const float* of = in.mode == ROW_IN_PAIR_U8 ? nullptr : in.f32 + base * in.unit_stride;
@@ -699,7 +712,7 @@ __attribute__((visibility("default"))) int fdr_plan_create(fdr_plan** plan, int 
             // is launch-bound and the extra launches cost more than the saved traffic); FDR_HALF=0 disables it
             const char* hv = getenv("FDR_HALF");
             const char* hm = getenv("FDR_HALF_MIN_PIXELS");
-            const long long min_px = (hm && atoll(hm) >= 0) ? atoll(hm) : (1LL << 21);
+            const long long min_px = (hm && atoll(hm) >= 0) ? atoll(hm) : (1LL << 22);
             p->half_ok = !(hv && atoi(hv) == 0) && p->Cp >= FDR_HALF_MIN_N && p->Rp >= 2 && (long long)p->Rp * p->Cp >= min_px;
             ColPassArgs probe{};
             probe.n = p->Rp;

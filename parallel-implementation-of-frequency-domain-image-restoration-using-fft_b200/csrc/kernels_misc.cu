@@ -200,6 +200,78 @@ __global__ void pack_u8_c3_vec4_kernel(const float* __restrict__ raw, long long 
     }
 }
 
+// The same pack for a FEW images with launch_minmax_finalize folded in: warps 0-2 of every CTA fold the slots of the image's three
+// planes and derive scale / shift exactly as minmax_finalize_kernel does; CTA 0 of an image also publishes them (last_minmax API).
+__global__ void pack_u8_c3_vec4_fused_kernel(const float* __restrict__ raw, long long ustride, const unsigned int* __restrict__ mm,
+                                             float2* __restrict__ ss_out, float* __restrict__ mmf_out, uint8_t* __restrict__ out,
+                                             long long nquads) {
+    __shared__ float2 kk[3];
+    const int img = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 3) {
+        const int u = img * 3 + warp;
+        const uint2* e = reinterpret_cast<const uint2*>(mm) + (size_t)u * FDR_MINMAX_SLOTS;
+        unsigned int lo = 0xFFFFFFFFu, hi = 0u;
+        for (int k = lane; k < FDR_MINMAX_SLOTS; k += 32) {
+            const uint2 v = e[k];
+            lo = min(lo, v.x);
+            hi = max(hi, v.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) {
+            const double smin = (double)f32_from_ordered(lo), smax = (double)f32_from_ordered(hi);
+            const double scale = (smax - smin) > DBL_EPSILON ? 1.0 / (smax - smin) : 0.0;
+            const float a = (float)scale;
+            const float b = 0.0f - (float)__dmul_rn(smin, (double)a);
+            kk[warp] = make_float2(a, b);
+            if (blockIdx.x == 0) {
+                ss_out[u] = make_float2(a, b);
+                if (mmf_out) {
+                    mmf_out[2 * u] = (float)smin;
+                    mmf_out[2 * u + 1] = (float)smax;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const float4* r0 = reinterpret_cast<const float4*>(raw + (long long)img * 3 * ustride);
+    const float4* r1 = reinterpret_cast<const float4*>(raw + ((long long)img * 3 + 1) * ustride);
+    const float4* r2 = reinterpret_cast<const float4*>(raw + ((long long)img * 3 + 2) * ustride);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + (long long)img * nquads * 12);
+    const float2 k0 = kk[0], k1 = kk[1], k2 = kk[2];
+    auto q8 = [](float v, float2 k) -> uint32_t {
+        int q = __float2int_rn(fmaf(v, k.x, k.y) * 255.0f);
+        return (uint32_t)min(max(q, 0), 255);
+    };
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < nquads; j += (long long)gridDim.x * blockDim.x) {
+        const float4 b = __ldg(r0 + j), g = __ldg(r1 + j), r = __ldg(r2 + j);
+        const uint32_t b0 = q8(b.x, k0), g0 = q8(g.x, k1), c0 = q8(r.x, k2);
+        const uint32_t b1 = q8(b.y, k0), g1 = q8(g.y, k1), c1 = q8(r.y, k2);
+        const uint32_t b2 = q8(b.z, k0), g2 = q8(g.z, k1), c2 = q8(r.z, k2);
+        const uint32_t b3 = q8(b.w, k0), g3 = q8(g.w, k1), c3 = q8(r.w, k2);
+        o[3 * j] = b0 | (g0 << 8) | (c0 << 16) | (b1 << 24);
+        o[3 * j + 1] = g1 | (c1 << 8) | (b2 << 16) | (g2 << 24);
+        o[3 * j + 2] = c2 | (b3 << 8) | (g3 << 16) | (c3 << 24);
+    }
+}
+bool pack_u8_c3_fused_applicable(const float* raw, long long raw_unit_stride, const uint8_t* out, int imgs, int channels, int rows, int cols) {
+    const long long npx = (long long)rows * cols;
+    return channels == 3 && imgs <= 2 && npx % 4 == 0 && raw_unit_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(raw) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+}
+cudaError_t launch_pack_u8_c3_fused(const float* raw, long long raw_unit_stride, const unsigned int* minmax, float2* scale_shift, float* minmax_f32,
+                                    uint8_t* out, int imgs, int rows, int cols, cudaStream_t s) {
+    const long long npx = (long long)rows * cols;
+    int bq = (int)((npx / 4 + 255) / 256);
+    if (bq > 148 * 8) bq = 148 * 8;
+    pack_u8_c3_vec4_fused_kernel<<<dim3(bq, imgs), 256, 0, s>>>(raw, raw_unit_stride, minmax, scale_shift, minmax_f32, out, npx / 4);
+    return cudaGetLastError();
+}
+
 __global__ void pack_u8_generic_kernel(const float* raw, long long ustride, const float2* ss, uint8_t* out, int C,
                                        int rows, int cols) {
     const int img = blockIdx.y;

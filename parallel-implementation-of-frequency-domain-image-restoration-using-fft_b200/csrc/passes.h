@@ -74,6 +74,8 @@ struct RowPassArgs {
     long long peer_plane;        // elements per pair in a slab = rows_padded * (n / world)
     int row0;                    // global (padded) index of local row 0
     int max_ctas;                // > 0: scatter / gather passes run as at most this many persistent CTAs per pair
+    unsigned int* mm_reset;      // != NULL: CTA 0 of every pair / plane re-arms the min/max slots of its planes (same layout as `minmax`;
+                                 // saves the separate reset launch; needs local_units)
     int prefetch_dist;           // long rows: L2 prefetch of the input of the row block this many blocks ahead (set by the launcher)
     // ---- half-plane forms (ROW_IN_ROWS2_*, ROW_OUT_HALF, ROW_IN_HALF, ROW_OUT_REAL_ROWS2): blockIdx.y counts PLANES ----
     int pair_dist;               // D: row `r` of the launch carries rows r and r + D (local indices, like `row0 + r` globally)
@@ -171,6 +173,10 @@ cudaError_t launch_normalize_f32(const float* raw, long long raw_unit_stride, co
 cudaError_t launch_synth_u8(uint8_t* out, uint32_t seed, long long img0, int imgs, int channels, long long plane_px,
                             long long px0, long long npx, cudaStream_t s);
 // negate_max / negated_max: the f32 vector holds (min, -max) per plane (one all-reduce(MIN) across ranks folds both)
+// pack of a few BGR images with the slot fold + scale/shift (launch_minmax_finalize) done by every CTA itself: one launch less
+cudaError_t launch_pack_u8_c3_fused(const float* raw, long long raw_unit_stride, const unsigned int* minmax, float2* scale_shift, float* minmax_f32,
+                                    uint8_t* out, int imgs, int rows, int cols, cudaStream_t s);
+bool pack_u8_c3_fused_applicable(const float* raw, long long raw_unit_stride, const uint8_t* out, int imgs, int channels, int rows, int cols);
 cudaError_t launch_minmax_decode(const unsigned int* minmax, float* minmax_f32, int units, int negate_max, cudaStream_t s);
 cudaError_t launch_scale_shift_from_f32(const float* minmax_f32, float2* scale_shift, int units, int negated_max, cudaStream_t s);
 // out[y] = column n/2 of the row spectrum of PSF row y (real): sum_x psf[y][x] * (-1)^x

@@ -402,6 +402,15 @@ template <int LOGN, int IN_MODE> __device__ __forceinline__ void row_prefetch_ne
 template <int LOGN, int IN_MODE, int OUT_MODE, bool CONJ>
 __global__ void __launch_bounds__(RowGeom<LOGN>::THREADS, RowGeom<LOGN>::MIN_BLOCKS) row_pass_kernel(const RowPassArgs a) {
     if constexpr (LOGN >= 13) row_prefetch_next<LOGN, IN_MODE>(a);
+    if (a.mm_reset && blockIdx.x == 0) {   // re-arm the extrema slots of this pair's planes (pass 3 of the same call fills them)
+        constexpr bool HALF = (IN_MODE == ROW_IN_ROWS2_F32 || IN_MODE == ROW_IN_ROWS2_U8);
+        const int pair = blockIdx.y + a.pair_base;
+        const int u0 = HALF ? pair : 2 * pair;
+        int nu = HALF ? 1 : 2;
+        if (u0 + nu > a.local_units) nu = a.local_units - u0;
+        uint2* e = reinterpret_cast<uint2*>(a.mm_reset) + (size_t)u0 * FDR_MINMAX_SLOTS;
+        for (int i = threadIdx.x; i < nu * FDR_MINMAX_SLOTS; i += blockDim.x) e[i] = make_uint2(0xFFFFFFFFu, 0u);
+    }
     row_pass_body<LOGN, IN_MODE, OUT_MODE, CONJ>(a, blockIdx.x);
 }
 

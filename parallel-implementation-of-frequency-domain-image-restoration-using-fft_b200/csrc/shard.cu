@@ -79,7 +79,7 @@ struct fdr_shard {
     // because the peers store into them in exchange 3.
     bool staged = false;
     size_t stage_off = 0, stage_nyq_off = 0;   // element offsets inside the slab allocation
-    int link_ctas = 16;
+    int link_ctas = 24;
     int link_mode = 0;          // 0: link kernel (bulk copies from link_ctas CTAs); 1: the device's copy engines (cudaMemcpyAsync per block)
     int ce_streams = 4;         // copy-engine mode: the blocks of one exchange are spread over this many streams (engines)
     cudaStream_t st_ce[8] = {};

@@ -341,7 +341,7 @@ def test_kernel_timing_api(gpu, oracle):
         p.set_kernel_timing(True)
         p.restore_images_u8(imgs)
         kt = p.kernel_timing()
-        assert p.last_launch_count() == 6
+        assert p.last_launch_count() == 4  # rows, columns, rows, pack (slot reset and fold ride along in pass 1 and the pack)
     assert all(kt[k]["launches"] == 1 and kt[k]["ms"] > 0 and kt[k]["bytes"] > 0 for k in kt)
 
 
