@@ -262,13 +262,21 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
     def step():
         drv.restore_rows(d_in.data_ptr(), d_out.data_ptr(), sh)
 
+    # Every restore contains cross-rank barriers, so every rank must run the SAME number of them: loop counts below are derived
+    # from a duration all-reduced over the ranks, never from a rank's own clock.
     t_w0 = time.perf_counter()
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
-    while time.perf_counter() - t_w0 < 1.5:   # keep the GPUs busy until the clock sampler has started reporting
+    tw = torch.tensor([(time.perf_counter() - t_w0) / max(1, warmup)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    per_step_s = max(float(tw.item()), 1e-4)
+    n_fill = int(min(3000, max(0, 1.5 / per_step_s)))   # ~1.5 s of the same load: the clock sampler needs ~1 s to start
+    for i in range(n_fill):
         step()
-        torch.cuda.synchronize()
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -283,11 +291,12 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / steps
     # a longer busy stretch of the same step so that the 200 ms sampler sees the clocks under this load
-    t_b0 = time.perf_counter()
-    while time.perf_counter() - t_b0 < 1.0:
-        for _ in range(20):
-            step()
-        torch.cuda.synchronize()
+    n_busy = int(min(3000, max(20, 1.0 / max(ms_step * 1e-3, 1e-4))))   # identical on every rank (ms_step is all-reduced)
+    for i in range(n_busy):
+        step()
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clocks = sampler.stop()
     dist.barrier()
 
@@ -560,6 +569,7 @@ def main():
                          "against this library's single-GPU path, or nothing")
     ap.add_argument("--no-sharded", action="store_true", help="N>1, batch workload: skip the row-sharded 16384^2 leg (BASELINE configs[4])")
     ap.add_argument("--sharded-steps", type=int, default=20)
+    ap.add_argument("--sharded-timeout", type=int, default=300, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
     ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
     args = ap.parse_args()
     claim_stdout()
@@ -717,20 +727,42 @@ def main():
         side = side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, value)
     _trace('side done')
     # ---- BASELINE configs[4] inside the same line when N > 1: one 16384^2 RGB image row-sharded over all ranks ----
-    sharded = None
-    if world > 1 and not args.no_sharded and args.workload == "batch256x2048":
+    run_shard_leg = world > 1 and not args.no_sharded and args.workload == "batch256x2048"
+    if run_shard_leg:
         del d_in, d_out
         plan.close()
         plan = None
         torch.cuda.empty_cache()
-        c4, _, H4, W4, pl4, pa4 = WORKLOADS["rgb16384"]
-        sharded = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, c4, H4, W4, pl4, pa4, 0xF17E0000 + c4,
+
+    def sharded_leg(line):
+        """The row-sharded 16384^2 measurement under a watchdog: whatever happens in it (a rank failing, a barrier that never
+        completes), rank 0 still prints the batch line -- with the reason instead of the numbers -- and every rank exits."""
+        def abort():
+            if rank == 0 and line is not None:
+                line["sharded"] = {"unavailable": "row-sharded leg did not finish within %d s" % args.sharded_timeout}
+                emit(line)
+            os._exit(0)
+        wd = threading.Timer(args.sharded_timeout, abort)
+        wd.daemon = True
+        wd.start()
+        try:
+            c4, _, H4, W4, pl4, pa4 = WORKLOADS["rgb16384"]
+            res = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, c4, H4, W4, pl4, pa4, 0xF17E0000 + c4,
                                   args.sharded_steps, max(3, args.warmup), want_e2e=not args.no_e2e,
                                   parity_mode="none" if args.no_check else args.sharded_parity)
+        except Exception as e:  # keep the batch line; the other ranks leave through their own watchdogs
+            res = {"unavailable": ("%s: %s" % (type(e).__name__, e))[:300]}
+        wd.cancel()
+        return res
 
     if rank != 0:
+        if run_shard_leg:
+            sharded_leg(None)
         if world > 1:
-            dist.destroy_process_group()
+            try:
+                dist.destroy_process_group()
+            except Exception:
+                pass
         return 0
 
     _trace('sharded leg done')
@@ -874,8 +906,8 @@ def main():
         line["cpu_baselines"] = cpu_baselines
     if side:
         line["side"] = side
-    if sharded:
-        line["sharded"] = sharded
+    if run_shard_leg:
+        line["sharded"] = sharded_leg(line)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
