@@ -50,7 +50,7 @@ def main():
     print("%-110s %s" % ("kernel", " ".join("%9s" % c[:9] for c in cols)))
     for k, c in counts.items():
         nm = re.sub(r"\s+", " ", names.get(k, k))
-        nm = re.sub(r"\(.*$", "", nm)[:108]
+        nm = re.sub(r"\(.*$", "", nm.replace("(anonymous namespace)::", ""))[:108]
         print("%-110s %s" % (nm, " ".join("%9d" % c[x] for x in cols)))
         tot.update(c)
     print("%-110s %s" % ("ALL KERNELS", " ".join("%9d" % tot[x] for x in cols)))
