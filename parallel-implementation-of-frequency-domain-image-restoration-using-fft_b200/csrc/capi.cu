@@ -1318,8 +1318,12 @@ __attribute__((visibility("default"))) int fdr_motion_psf_host(int length, doubl
     if (length < 1 || !psf_out) return set_error(FDR_E_INVALID, "bad PSF arguments");
     float* d = nullptr;
     FDR_CUDA(cudaMalloc(&d, sizeof(float) * (size_t)length * length));
-    cudaError_t e = launch_motion_psf(d, length, motion_affine(length, angle_deg), 0);
-    if (e == cudaSuccess) e = cudaMemcpy(psf_out, d, sizeof(float) * (size_t)length * length, cudaMemcpyDeviceToHost);
+    cudaStream_t st = nullptr;   // own non-blocking stream: nothing of this library runs on the legacy default stream
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = launch_motion_psf(d, length, motion_affine(length, angle_deg), st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(psf_out, d, sizeof(float) * (size_t)length * length, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (st) cudaStreamDestroy(st);
     cudaFree(d);
     if (e != cudaSuccess) return set_error(FDR_E_CUDA, "motion PSF: %s", cudaGetErrorString(e));
     return FDR_OK;

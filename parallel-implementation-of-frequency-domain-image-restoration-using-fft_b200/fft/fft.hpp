@@ -21,6 +21,10 @@
 using namespace cv;
 using namespace std;
 
+// NOTE on semantics (not on the signatures, which are the reference's): these functions normalise every channel over the PADDED
+// plane and then crop, exactly as the serial path does (fft_serial.cpp:246-258) -- the reference's own gpu mode crops first and
+// normalises the cropped plane (fft_gpu.cu:361-381).  For images whose sizes are powers of two the two are identical; otherwise the
+// result matches serial.cpp / the --impl serial output, which is the parity contract of this path.
 namespace fft_gpu {
     void wienerDeblur_RGB_naive(vector<Mat>& channels, const Mat& psf, float K);
     void wienerDeblur_RGB_optimized(vector<Mat>& channels, const Mat& psf, float K);
