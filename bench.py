@@ -569,7 +569,7 @@ def main():
                          "against this library's single-GPU path, or nothing")
     ap.add_argument("--no-sharded", action="store_true", help="N>1, batch workload: skip the row-sharded 16384^2 leg (BASELINE configs[4])")
     ap.add_argument("--sharded-steps", type=int, default=20)
-    ap.add_argument("--sharded-timeout", type=int, default=300, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
+    ap.add_argument("--sharded-timeout", type=int, default=200, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
     ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
     args = ap.parse_args()
     claim_stdout()
