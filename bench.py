@@ -238,6 +238,43 @@ def pcie_roofline(torch, dist, dev, world, mb=256, reps=4):
             "how": "%d MiB pinned H2D and D2H concurrently on two streams, x%d, all %d ranks at once, slowest rank" % (mb, reps, world)}
 
 
+def sharded_parity(fdr, torch, got, mode, cfg_idx, H, W, plen, pang, seed, dev, local_rank, sh):
+    """Rank 0: the gathered result against (mode "oracle") plane 0 of the WHOLE image restored by the reference's CPU code at
+    full size -- oracle/_ref openmp mode, which agrees with its serial mode to 1e-7; the serial port otherwise
+    (fft_serial.cpp:141-261) -- or (mode "self") the whole image restored by this library's single-GPU path."""
+    import numpy as np
+    if mode == "oracle":
+        O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+        psf = O.port().motion_psf(plen, pang)
+        img0 = O.synth_image_u8(cfg_idx, 0, H, W, channels=1)[0]
+        pl = O.pad_pow2(img0.astype(np.float32) * np.float32(1.0 / 255.0))
+        t0 = time.perf_counter()
+        if O.have_ref():
+            O.ref().set_threads(os.cpu_count() or 1)
+            norm = O.ref().wiener(pl, psf, K_WIENER, "openmp")[:H, :W]
+            how = "reference fft_openmp.cpp compiled unmodified (oracle/_ref), %d threads" % (os.cpu_count() or 1)
+        else:
+            norm = O.port().wiener_deblur(pl, psf, K_WIENER)["norm"][:H, :W]
+            how = "oracle port (serial)"
+        t_cpu = time.perf_counter() - t0
+        want = O.port().pack_u8(norm)
+        against = "%s on the whole %dx%d plane 0, %.1f s" % (how, H, W, t_cpu)
+    else:
+        whole = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+        ref_out = torch.empty_like(whole)
+        fdr.synth_images_device_u8(whole.data_ptr(), seed, 0, 1, 3, H, W, sh)
+        with fdr.Plan(H, W, 3, 1, local_rank) as plan:
+            plan.set_psf_motion(plen, pang, K_WIENER)
+            plan.restore_images_device_u8(whole.data_ptr(), ref_out.data_ptr(), 1, sh)
+            torch.cuda.synchronize()
+        want = ref_out.cpu().numpy()
+        against = "single-GPU path of this library, whole image"
+        del whole, ref_out
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    return {"against": against, "pixels": int(d.size), "exact": int((d == 0).sum()), "off_by_1": int((d == 1).sum()),
+            "off_by_more": int((d > 1).sum()), "frac_within_1": float((d <= 1).mean())}
+
+
 def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H, W, plen, pang, seed, steps, warmup,
                     want_e2e=True, parity_mode="oracle"):
     """One image row-sharded over `world` GPUs (BASELINE configs[4]); strong scaling.  The transposes of the reference's
@@ -390,37 +427,11 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
         parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)
         if rank == 0:
-            got = torch.cat(parts)[:H].cpu().numpy()
-            if parity_mode == "oracle":
-                O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
-                psf = O.port().motion_psf(plen, pang)
-                img0 = O.synth_image_u8(cfg_idx, 0, H, W)[0]
-                pl = O.pad_pow2(img0.astype(np.float32) * np.float32(1.0 / 255.0))
-                t0 = time.perf_counter()
-                if O.have_ref():
-                    O.ref().set_threads(os.cpu_count() or 1)
-                    norm = O.ref().wiener(pl, psf, K_WIENER, "openmp")[:H, :W]
-                    how = "reference fft_openmp.cpp compiled unmodified (oracle/_ref), %d threads" % (os.cpu_count() or 1)
-                else:
-                    norm = O.port().wiener_deblur(pl, psf, K_WIENER)["norm"][:H, :W]
-                    how = "oracle port (serial)"
-                t_cpu = time.perf_counter() - t0
-                want = O.port().pack_u8(norm)
-                against = "%s on the whole %dx%d plane 0, %.1f s" % (how, H, W, t_cpu)
-            else:
-                whole = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
-                ref_out = torch.empty_like(whole)
-                fdr.synth_images_device_u8(whole.data_ptr(), seed, 0, 1, 3, H, W, sh)
-                with fdr.Plan(H, W, 3, 1, local_rank) as plan:
-                    plan.set_psf_motion(plen, pang, K_WIENER)
-                    plan.restore_images_device_u8(whole.data_ptr(), ref_out.data_ptr(), 1, sh)
-                    torch.cuda.synchronize()
-                want = ref_out.cpu().numpy()
-                against = "single-GPU path of this library, whole image"
-                del whole, ref_out
-            d = np.abs(got.astype(np.int16) - want.astype(np.int16))
-            parity = {"against": against, "pixels": int(d.size), "exact": int((d == 0).sum()), "off_by_1": int((d == 1).sum()),
-                      "off_by_more": int((d > 1).sum()), "frac_within_1": float((d <= 1).mean())}
+            try:   # rank-0-only work: a failure here must not skip the collectives below (the other ranks wait in them)
+                parity = sharded_parity(fdr, torch, torch.cat(parts)[:H].cpu().numpy(), parity_mode, cfg_idx, H, W, plen, pang, seed,
+                                        dev, local_rank, sh)
+            except Exception as e:
+                parity = {"error": ("%s: %s" % (type(e).__name__, e))[:300]}
         dist.barrier()
     timed_out = back.sync_timed_out(sh)
     launches = back.last_launch_count()
@@ -456,6 +467,8 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
                        "target_frac": 0.60, "target_ms": CONTRACT_BYTES_PER_CHANNEL_PIXEL * chan_px / (0.60 * peak * world * 1e9) * 1e3},
         "e2e": e2e, "gpu_launches_per_step": int(launches), "clocks": clocks, "parity": parity, "barrier_timed_out": bool(timed_out),
     }
+    if timed_out:
+        res["invalid"] = "a cross-rank barrier gave up after its 20 s time-out (a peer never arrived): the numbers above are not a measurement"
     return res
 
 
@@ -569,7 +582,7 @@ def main():
                          "against this library's single-GPU path, or nothing")
     ap.add_argument("--no-sharded", action="store_true", help="N>1, batch workload: skip the row-sharded 16384^2 leg (BASELINE configs[4])")
     ap.add_argument("--sharded-steps", type=int, default=20)
-    ap.add_argument("--sharded-timeout", type=int, default=200, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
+    ap.add_argument("--sharded-timeout", type=int, default=300, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
     ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
     args = ap.parse_args()
     claim_stdout()
@@ -738,10 +751,12 @@ def main():
         """The row-sharded 16384^2 measurement under a watchdog: whatever happens in it (a rank failing, a barrier that never
         completes), rank 0 still prints the batch line -- with the reason instead of the numbers -- and every rank exits."""
         def abort():
-            if rank == 0 and line is not None:
-                line["sharded"] = {"unavailable": "row-sharded leg did not finish within %d s" % args.sharded_timeout}
-                emit(line)
-            os._exit(0)
+            try:
+                if rank == 0 and line is not None:
+                    line["sharded"] = {"unavailable": "row-sharded leg did not finish within %d s" % args.sharded_timeout}
+                    emit(line)
+            finally:
+                os._exit(0)
         wd = threading.Timer(args.sharded_timeout, abort)
         wd.daemon = True
         wd.start()
@@ -755,14 +770,23 @@ def main():
         wd.cancel()
         return res
 
-    if rank != 0:
-        if run_shard_leg:
-            sharded_leg(None)
+    def leave_group():
+        """The line is out (or this rank has none to print): tear the process group down, but never wait for it -- after a
+        failed sharded leg a peer may be gone, and an NCCL teardown that waits for it would keep the launcher alive."""
         if world > 1:
+            t = threading.Timer(30.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
             try:
                 dist.destroy_process_group()
             except Exception:
                 pass
+            t.cancel()
+
+    if rank != 0:
+        if run_shard_leg:
+            sharded_leg(None)
+        leave_group()
         return 0
 
     _trace('sharded leg done')
@@ -909,8 +933,7 @@ def main():
     if run_shard_leg:
         line["sharded"] = sharded_leg(line)
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    leave_group()
     return 0
 
 

@@ -1,0 +1,109 @@
+"""CPU test of bench.py's multi-rank line: `python -m torch.distributed.run --nproc-per-node 2 tests/fake_gpu_bench.py ...`
+launches bench.main() exactly as the driver launches bench.py, with the device layer replaced by CPU stand-ins
+(tests/fake_gpu_bench.py) and gloo instead of NCCL.  What is checked is the host logic a GPU box cannot be spared for:
+every rank issues the same number of restores (loop counts come from all-reduced durations), the `sharded` object and the
+contract keys are in the ONE line rank 0 prints, and the watchdog keeps that line when the row-sharded leg hangs or fails."""
+import json
+import os
+import stat
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytest.importorskip("torch")
+
+FAKE_SMI = """#!/bin/bash
+while true; do echo "1965, 1965, 512.3, Not Active, Not Active, Not Active, Active"; sleep 0.2; done
+"""
+
+
+def run_fake_bench(tmp_path, port, extra_args=(), extra_env=None, nproc=2):
+    bindir = tmp_path / "bin"
+    bindir.mkdir(exist_ok=True)
+    smi = bindir / "nvidia-smi"
+    smi.write_text(FAKE_SMI)
+    smi.chmod(smi.stat().st_mode | stat.S_IEXEC)
+    shared = tmp_path / "shared"
+    shared.mkdir(exist_ok=True)
+    env = dict(os.environ)
+    env["PATH"] = str(bindir) + os.pathsep + env.get("PATH", "")
+    env["FAKE_TMP"] = str(shared)
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "fake_gpu_bench.py"), "--gpus", str(nproc), "--steps", "2",
+           "--warmup", "3"] + list(extra_args)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    return r, lines
+
+
+def base_port():
+    return 29800 + os.getpid() % 1500
+
+
+def test_two_rank_line_carries_the_sharded_leg(tmp_path):
+    r, lines = run_fake_bench(tmp_path, base_port())
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1, "stdout must hold exactly ONE line: %r" % lines   # the contract
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "parity", "sharded"):
+        assert k in d, k
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["config"]["workload"] == "batch256x2048"
+    assert d["clocks"]["samples"] > 0 and d["clocks"]["reasons"] == ["sw_power_cap"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["roofline"]["bound"] == "pcie"
+    assert d["parity"]["off_by_more"] == 0 and len(d["parity"]["more_images"]) >= 1
+    s = d["sharded"]
+    assert "unavailable" not in s, s
+    assert s["n_gpus"] == 2 and s["scaling"] == "strong" and s["steps"] == 20
+    assert s["clocks"]["samples"] > 0
+    assert s["barrier_timed_out"] is False and "invalid" not in s
+    assert s["parity"]["frac_within_1"] >= 0.999 and s["parity"]["off_by_more"] == 0   # against the reference CPU code
+    assert s["e2e"]["matches_device"] is True and s["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(s["phases_ms_serial_schedule"]) == {"phase1_rows_fwd", "exchange1_push", "phase2_cols_wiener", "exchange3_push",
+                                                   "phase3_rows_inv", "phase4_pack", "total"}
+    assert s["contract53"]["target_frac"] == 0.60
+
+
+def test_watchdog_keeps_the_batch_line_when_a_rank_hangs(tmp_path):
+    r, lines = run_fake_bench(tmp_path, base_port() + 1, ["--sharded-timeout", "6"], {"FAKE_HANG_RANK": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] > 0 and d["n_gpus"] == 2
+    # rank 0's own watchdog, or -- the hung rank's watchdog having fired first -- the collective that lost its peer
+    assert "unavailable" in d["sharded"]
+
+
+@pytest.mark.parametrize("bad_rank", [0, 1])
+def test_failure_inside_the_sharded_leg_keeps_the_batch_line(tmp_path, bad_rank):
+    r, lines = run_fake_bench(tmp_path, base_port() + 2 + bad_rank, ["--sharded-timeout", "6"], {"FAKE_RAISE_RANK": str(bad_rank)})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] > 0 and "unavailable" in d["sharded"]
+
+
+def test_single_rank_line(tmp_path):
+    env = {"FDR_BENCH_TRACE": "0"}
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    smi = bindir / "nvidia-smi"
+    smi.write_text(FAKE_SMI)
+    smi.chmod(smi.stat().st_mode | stat.S_IEXEC)
+    (tmp_path / "shared").mkdir()
+    e = dict(os.environ, PATH=str(bindir) + os.pathsep + os.environ.get("PATH", ""), FAKE_TMP=str(tmp_path / "shared"), **env)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "fake_gpu_bench.py"), "--steps", "2", "--warmup", "3"],
+                       capture_output=True, text=True, env=e, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 1 and "sharded" not in d
+    assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"]
+    assert d["roofline"]["kernel"] == "pass2_cols_wiener" and d["roofline"]["isolated"]["frac"] > 0
+    assert {"serial", "simd", "openmp"} <= set(d.get("cpu_baselines", {"serial": 0, "simd": 0, "openmp": 0}))
