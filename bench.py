@@ -35,6 +35,7 @@ WORKLOADS = {
     "cat": (0, 1, 782, 1920, 50, 30.0),
 }
 K_WIENER = 0.01
+CHILD_ENTRY = os.path.abspath(__file__)   # what sharded_leg_isolated launches (the CPU test harness points it at itself)
 CONTRACT_BYTES_PER_CHANNEL_PIXEL = 53.0
 
 
@@ -438,7 +439,8 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
     half = back.half_plane
     back_staged = bool(getattr(back, "staged", False))
     Rp, Cp = back.padded_rows, back.padded_cols
-    back.close()
+    peer_sync, native = bool(drv.peer_sync), bool(drv.native)
+    drv.close()   # collective: every rank unmaps its peers' slabs before any rank frees its own
     peak, peak_src = measured_peak_gbs()
     planes_c = 1.5 if half else 2.0                                   # complex planes through the exchange and the column phase
     col_bytes_px = 56.0 if Rp >= 8192 else 24.0                       # K x 2048 block scheme: three sweeps
@@ -452,8 +454,8 @@ def sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_id
     res = {
         "workload": "rgb16384" if H == 16384 else "%dx%dx3" % (H, W), "image": [H, W, 3], "n_gpus": world,
         "ms_per_step": ms_step, "value": H * W / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s", "steps": steps, "warmup": warmup,
-        "scaling": "strong", "half_plane": bool(half), "staged_exchanges": staged, "peer_sync": bool(drv.peer_sync),
-        "driver": "fdr_shard_restore_rows (native, pipelined over the colour planes)" if (drv.peer_sync and drv.native) else "python unit pipeline",
+        "scaling": "strong", "half_plane": bool(half), "staged_exchanges": staged, "peer_sync": peer_sync,
+        "driver": "fdr_shard_restore_rows (native, pipelined over the colour planes)" if (peer_sync and native) else "python unit pipeline",
         "phases_ms_serial_schedule": dict(zip(names + ["total"], ph)),
         "phase2_hbm": {"bytes_per_gpu": bytes_p2, "GBps": bytes_p2 / (ph[2] * 1e-3) / 1e9 if ph[2] > 0 else None,
                        "frac_of_peak": bytes_p2 / (ph[2] * 1e-3) / 1e9 / peak if ph[2] > 0 else None, "peak": peak, "peak_source": peak_src},
@@ -479,7 +481,7 @@ def run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H
     r = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H, W, plen, pang, seed, args.steps, args.warmup,
                         want_e2e=not args.no_e2e, parity_mode="none" if args.no_check else args.sharded_parity)
     if rank != 0:
-        dist.destroy_process_group()
+        leave_group(dist, world)
         return 0
     line = {
         "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
@@ -498,8 +500,99 @@ def run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H
         "cpu_baseline": None, "parity": r["parity"], "sharded": r,
     }
     emit(line)
-    dist.destroy_process_group()
+    leave_group(dist, world)
     return 0
+
+
+def leave_group(dist, world):
+    """The line is out (or this rank has none to print): tear the process group down, but never wait for it -- after a failed
+    sharded leg a peer may be gone, and an NCCL teardown that waits for it would keep the launcher alive."""
+    if world > 1:
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        t.cancel()
+
+
+def run_sharded_child(args, fdr, torch, dist, world, rank, local_rank, dev):
+    """--sharded-child PATH: the row-sharded 16384^2 leg of the batch line in its OWN process group (one child per rank,
+    spawned by sharded_leg_isolated below).  Rank 0 writes the result object to PATH; nothing goes to stdout."""
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    c4, _, H4, W4, pl4, pa4 = WORKLOADS["rgb16384"]
+    try:
+        res = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, c4, H4, W4, pl4, pa4, 0xF17E0000 + c4,
+                              args.sharded_steps, max(3, args.warmup), want_e2e=not args.no_e2e,
+                              parity_mode="none" if args.no_check else args.sharded_parity)
+    except Exception as e:
+        res = {"unavailable": ("%s: %s" % (type(e).__name__, e))[:300]}
+    if rank == 0:
+        tmp = args.sharded_child + ".tmp"
+        with open(tmp, "w") as f:
+            json.dump(res, f)
+        os.replace(tmp, args.sharded_child)
+    leave_group(dist, world)
+    return 0
+
+
+def sharded_leg_isolated(args, dist, world, rank):
+    """The row-sharded leg as child processes with their own process group (every rank of this job spawns one child on its
+    GPU and waits for it): a crash, a hang or a CUDA error in that leg can then not take the batch measurement -- the line
+    rank 0 is about to print -- with it.  Collective over the parent group (one broadcast).  Returns the result on rank 0."""
+    import socket
+    import tempfile
+    info = [None]
+    if rank == 0:
+        sk = socket.socket()
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+        sk.close()
+        fd, path = tempfile.mkstemp(prefix="fdr_sharded_", suffix=".json")
+        os.close(fd)
+        os.unlink(path)
+        info = [(port, path)]
+    dist.broadcast_object_list(info, src=0)
+    port, path = info[0]
+    # the children rendezvous among themselves: no elastic-agent store, a fresh port (child rank 0 hosts the store)
+    env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}
+    env["MASTER_ADDR"] = "127.0.0.1"
+    env["MASTER_PORT"] = str(port)
+    cmd = [sys.executable, CHILD_ENTRY, "--sharded-child", path, "--gpus", str(world), "--warmup", str(args.warmup),
+           "--sharded-steps", str(args.sharded_steps), "--e2e-steps", str(args.e2e_steps), "--sharded-parity", args.sharded_parity]
+    cmd += (["--no-e2e"] if args.no_e2e else []) + (["--no-check"] if args.no_check else [])
+    t0 = time.perf_counter()
+    why = None
+    try:
+        p = subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL)
+        try:
+            rc = p.wait(timeout=args.sharded_timeout)
+            if rc != 0:
+                why = "child of rank %d exited with code %s" % (rank, rc)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            p.wait()
+            why = "did not finish within %d s" % args.sharded_timeout
+    except Exception as e:
+        why = "could not start the child: %s" % e
+    if rank != 0:
+        return None
+    res = None
+    try:
+        if os.path.exists(path):
+            with open(path) as f:
+                res = json.load(f)
+            os.unlink(path)
+    except Exception as e:
+        why = "unreadable result: %s" % e
+    if not isinstance(res, dict):
+        res = {"unavailable": "row-sharded leg (child processes): %s" % (why or "no result written")}
+    res["isolation"] = ("own process group, one child process per rank on the same GPUs (a failure in this leg cannot take the batch "
+                        "measurement with it); %.0f s including start-up" % (time.perf_counter() - t0))
+    return res
 
 
 def side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, our_value):
@@ -583,6 +676,8 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="N>1, batch workload: skip the row-sharded 16384^2 leg (BASELINE configs[4])")
     ap.add_argument("--sharded-steps", type=int, default=20)
     ap.add_argument("--sharded-timeout", type=int, default=300, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
+    ap.add_argument("--sharded-inprocess", action="store_true", help="run the row-sharded leg inside the ranks of this job instead of child processes")
+    ap.add_argument("--sharded-child", default="", help=argparse.SUPPRESS)   # internal: see run_sharded_child
     ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
     args = ap.parse_args()
     claim_stdout()
@@ -609,6 +704,8 @@ def main():
     B = args.images or images
     seed = 0xF17E0000 + cfg_idx
     dev = torch.device("cuda", local_rank)
+    if args.sharded_child:
+        return run_sharded_child(args, fdr, torch, dist, world, rank, local_rank, dev)
     if world > 1 and images == 1 and not args.replicas:
         return run_sharded(args, fdr, torch, dist, world, rank, local_rank, dev, cfg_idx, H, W, plen, pang, seed)
     stream = torch.cuda.Stream(device=dev)  # explicit non-default stream: kernels, events and copies all on it
@@ -748,8 +845,16 @@ def main():
         torch.cuda.empty_cache()
 
     def sharded_leg(line):
-        """The row-sharded 16384^2 measurement under a watchdog: whatever happens in it (a rank failing, a barrier that never
-        completes), rank 0 still prints the batch line -- with the reason instead of the numbers -- and every rank exits."""
+        """The row-sharded 16384^2 measurement.  Default: child processes with their own process group (sharded_leg_isolated).
+        --sharded-inprocess: in this process under a watchdog -- whatever happens in it short of a crash (a rank failing, a
+        barrier that never completes), rank 0 still prints the batch line, with the reason instead of the numbers, and every
+        rank exits."""
+        if not args.sharded_inprocess:
+            try:
+                return sharded_leg_isolated(args, dist, world, rank)
+            except Exception as e:
+                return {"unavailable": ("%s: %s" % (type(e).__name__, e))[:300]}
+
         def abort():
             try:
                 if rank == 0 and line is not None:
@@ -770,23 +875,10 @@ def main():
         wd.cancel()
         return res
 
-    def leave_group():
-        """The line is out (or this rank has none to print): tear the process group down, but never wait for it -- after a
-        failed sharded leg a peer may be gone, and an NCCL teardown that waits for it would keep the launcher alive."""
-        if world > 1:
-            t = threading.Timer(30.0, lambda: os._exit(0))
-            t.daemon = True
-            t.start()
-            try:
-                dist.destroy_process_group()
-            except Exception:
-                pass
-            t.cancel()
-
     if rank != 0:
         if run_shard_leg:
             sharded_leg(None)
-        leave_group()
+        leave_group(dist, world)
         return 0
 
     _trace('sharded leg done')
@@ -933,7 +1025,7 @@ def main():
     if run_shard_leg:
         line["sharded"] = sharded_leg(line)
     emit(line)
-    leave_group()
+    leave_group(dist, world)
     return 0
 
 

@@ -173,7 +173,9 @@ int fdr_shard_geometry(const fdr_shard* shard, int* first_row, int* n_rows, int*
 /* This rank's column slab (device pointer) for export to the peers. */
 int fdr_shard_local_slab(const fdr_shard* shard, void** d_slab, size_t* bytes);
 /* CUDA IPC plumbing for one-process-per-GPU runs: 64-byte handles travel through any host
- * channel (torch.distributed all_gather_object). */
+ * channel (torch.distributed all_gather_object, MPI_Allgather).  Tear-down order: every rank closes the
+ * handles it opened (fdr_ipc_close), a cross-rank barrier, and only then fdr_shard_destroy -- CUDA leaves
+ * freeing exported memory that a peer still has mapped undefined. */
 int fdr_ipc_export(const void* dptr, unsigned char handle[64]);
 int fdr_ipc_open(const unsigned char handle[64], void** dptr);
 int fdr_ipc_close(void* dptr);

@@ -305,11 +305,17 @@ class Shard:
         self.first_row, self.n_rows, self.padded_rows, self.padded_cols, self.cols_per_rank = [x.value for x in v]
         self._opened = []
 
+    def close_peers(self):
+        """Unmap the peers' slabs (fdr_ipc_close).  With several processes, every rank must have done this BEFORE any rank
+        frees its slab (close()): CUDA leaves freeing exported memory that a peer still has mapped undefined -- put a
+        cross-rank barrier between the two."""
+        for ptr in self._opened:
+            lib().fdr_ipc_close(ptr)
+        self._opened = []
+
     def close(self):
         if self.h:
-            for ptr in self._opened:
-                lib().fdr_ipc_close(ptr)
-            self._opened = []
+            self.close_peers()
             lib().fdr_shard_destroy(self.h)
             self.h = None
 

@@ -99,6 +99,16 @@ class ShardedRestorer:
                 torch.cuda.synchronize()
             dist.barrier(group=self.group)
 
+    def close(self):
+        """Collective tear-down: every rank unmaps its peers' slabs, THEN (after a cross-rank fence) frees its own -- CUDA IPC
+        leaves freeing exported memory that a peer still has mapped undefined (the reference's MPI_Finalize ordering,
+        mpi.cpp:124-127, has no such constraint because it never shares device memory)."""
+        if hasattr(self.b, "close_peers"):
+            self.b.close_peers()
+        self._fence()
+        self._mm = None
+        self.b.close()
+
     def barrier(self, flag=None, set_index=0, stream=None):
         """Stream-ordered cross-rank barrier: flags in peer memory (fdr_shard_barrier) when the backend has them and
         `peer_sync` is on, else a 1-element all-reduce on the current stream through torch.distributed."""

@@ -10,7 +10,8 @@ all-reduced durations, gathers, the JSON line, the watchdog) executes under gloo
 reachable from the product or from bench.py itself: the stand-ins are installed by this file only.
 
 Environment: FAKE_TMP (directory shared by the ranks), FAKE_HANG_RANK (that rank never returns from phase 1 of the sharded
-leg: exercises the watchdog), FAKE_RAISE_RANK (that rank raises inside the sharded leg)."""
+leg: exercises the watchdog), FAKE_RAISE_RANK (that rank raises inside the sharded leg), FAKE_CRASH_RANK (that rank's process
+kills itself inside the sharded leg)."""
 import contextlib
 import ctypes
 import os
@@ -221,6 +222,9 @@ class FakeShard:
         self.mm = np.zeros((channels, 2), np.float32)
         self.launches = 0
 
+    def close_peers(self):
+        self.peers = []
+
     def close(self):
         pass
 
@@ -243,6 +247,8 @@ class FakeShard:
     def phase1(self, d_in_rows, stream=0, pair=None):
         if os.environ.get("FAKE_HANG_RANK") == str(self.rank):
             time.sleep(10 ** 6)
+        if os.environ.get("FAKE_CRASH_RANK") == str(self.rank):
+            os.kill(os.getpid(), 9)
         if os.environ.get("FAKE_RAISE_RANK") == str(self.rank):
             raise RuntimeError("injected failure on rank %d" % self.rank)
         self.launches = 0
@@ -344,6 +350,7 @@ def main():
         return mod
 
     bench._load = load
+    bench.CHILD_ENTRY = os.path.abspath(__file__)   # the children of the isolated sharded leg need the same stand-ins
     small = int(os.environ.get("FAKE_SIZE", "48"))
     bench.WORKLOADS = dict(bench.WORKLOADS)
     bench.WORKLOADS["batch256x2048"] = (3, 2, small, small + 16, 5, 30.0)

@@ -44,8 +44,11 @@ def base_port():
     return 29800 + os.getpid() % 1500
 
 
-def test_two_rank_line_carries_the_sharded_leg(tmp_path):
-    r, lines = run_fake_bench(tmp_path, base_port())
+@pytest.mark.parametrize("inprocess", [False, True])
+def test_two_rank_line_carries_the_sharded_leg(tmp_path, inprocess):
+    """Default: the row-sharded leg runs as child processes with their own process group; --sharded-inprocess: inside the
+    ranks of the job, under the watchdog."""
+    r, lines = run_fake_bench(tmp_path, base_port() + (10 if inprocess else 0), ["--sharded-inprocess"] if inprocess else [])
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(lines) == 1, "stdout must hold exactly ONE line: %r" % lines   # the contract
     d = json.loads(lines[0])
@@ -66,10 +69,14 @@ def test_two_rank_line_carries_the_sharded_leg(tmp_path):
     assert set(s["phases_ms_serial_schedule"]) == {"phase1_rows_fwd", "exchange1_push", "phase2_cols_wiener", "exchange3_push",
                                                    "phase3_rows_inv", "phase4_pack", "total"}
     assert s["contract53"]["target_frac"] == 0.60
+    assert ("isolation" in s) == (not inprocess)
 
 
-def test_watchdog_keeps_the_batch_line_when_a_rank_hangs(tmp_path):
-    r, lines = run_fake_bench(tmp_path, base_port() + 1, ["--sharded-timeout", "6"], {"FAKE_HANG_RANK": "1"})
+@pytest.mark.parametrize("inprocess", [False])
+def test_batch_line_survives_a_hung_rank(tmp_path, inprocess):
+    r, lines = run_fake_bench(tmp_path, base_port() + (11 if inprocess else 1),
+                              ["--sharded-timeout", "12" if not inprocess else "6"] + (["--sharded-inprocess"] if inprocess else []),
+                              {"FAKE_HANG_RANK": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(lines) == 1
     d = json.loads(lines[0])
@@ -78,9 +85,21 @@ def test_watchdog_keeps_the_batch_line_when_a_rank_hangs(tmp_path):
     assert "unavailable" in d["sharded"]
 
 
-@pytest.mark.parametrize("bad_rank", [0, 1])
-def test_failure_inside_the_sharded_leg_keeps_the_batch_line(tmp_path, bad_rank):
-    r, lines = run_fake_bench(tmp_path, base_port() + 2 + bad_rank, ["--sharded-timeout", "6"], {"FAKE_RAISE_RANK": str(bad_rank)})
+@pytest.mark.parametrize("bad_rank,inprocess", [(0, False), (1, True)])
+def test_failure_inside_the_sharded_leg_keeps_the_batch_line(tmp_path, bad_rank, inprocess):
+    r, lines = run_fake_bench(tmp_path, base_port() + 2 + bad_rank + (10 if inprocess else 0),
+                              ["--sharded-timeout", "20" if not inprocess else "6"] + (["--sharded-inprocess"] if inprocess else []),
+                              {"FAKE_RAISE_RANK": str(bad_rank)})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] > 0 and "unavailable" in d["sharded"]
+
+
+def test_batch_line_survives_a_crashing_child(tmp_path):
+    """A child that dies outright (SIGKILL itself in phase 1) -- the case the in-process form cannot survive, because the
+    launcher tears every rank down when one dies."""
+    r, lines = run_fake_bench(tmp_path, base_port() + 5, ["--sharded-timeout", "20"], {"FAKE_CRASH_RANK": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(lines) == 1
     d = json.loads(lines[0])
