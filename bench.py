@@ -521,6 +521,15 @@ def leave_group(dist, world):
 def run_sharded_child(args, fdr, torch, dist, world, rank, local_rank, dev):
     """--sharded-child PATH: the row-sharded 16384^2 leg of the batch line in its OWN process group (one child per rank,
     spawned by sharded_leg_isolated below).  Rank 0 writes the result object to PATH; nothing goes to stdout."""
+    try:   # never outlive the rank that spawned this child (PR_SET_PDEATHSIG), nor the time that rank allows it
+        import ctypes
+        import signal
+        ctypes.CDLL(None).prctl(1, int(signal.SIGKILL))
+    except Exception:
+        pass
+    limit = threading.Timer(args.sharded_timeout + 30.0, lambda: os._exit(3))
+    limit.daemon = True
+    limit.start()
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     c4, _, H4, W4, pl4, pa4 = WORKLOADS["rgb16384"]
@@ -562,7 +571,8 @@ def sharded_leg_isolated(args, dist, world, rank):
     env["MASTER_ADDR"] = "127.0.0.1"
     env["MASTER_PORT"] = str(port)
     cmd = [sys.executable, CHILD_ENTRY, "--sharded-child", path, "--gpus", str(world), "--warmup", str(args.warmup),
-           "--sharded-steps", str(args.sharded_steps), "--e2e-steps", str(args.e2e_steps), "--sharded-parity", args.sharded_parity]
+           "--sharded-steps", str(args.sharded_steps), "--e2e-steps", str(args.e2e_steps), "--sharded-parity", args.sharded_parity,
+           "--sharded-timeout", str(args.sharded_timeout)]
     cmd += (["--no-e2e"] if args.no_e2e else []) + (["--no-check"] if args.no_check else [])
     t0 = time.perf_counter()
     why = None
