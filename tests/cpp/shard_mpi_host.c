@@ -48,6 +48,7 @@ struct cfg {
 static void rank_main(void* arg) {
     const struct cfg* c = (const struct cfg*)arg;
     int rank = 0, world = 1, ndev = 0;
+    alarm(100); /* test program: a rank that is stuck (a peer died) must not keep a GPU busy */
     MPI_Comm_rank(MPI_COMM_WORLD, &rank);
     MPI_Comm_size(MPI_COMM_WORLD, &world);
     CHECK_FDR(fdr_device_count(&ndev));

@@ -4,8 +4,9 @@ path, which the in-process emulation of test_gpu_sharded.py cannot show.  On a o
 barrier kernels take turns through the driver's time slicing), so this is a functional check only.
 
 CPU part: the program compiles and links against include/fdr_b200.h + libfdr_b200.so and fails loudly without a device.
-GPU part: written after this round's GPU budget was spent, hence never run before the round-end suite: marked xfail(strict=False)
-so that an environment limit of multi-process sharing on one GPU cannot mask the rest of the suite (XPASS = it works)."""
+GPU part: written after this round's GPU budget was spent, so it has never run.  Several processes spinning in barrier kernels on
+ONE device depend on the driver's time slicing between contexts; if that misbehaves, the ranks have to be killed with kernels
+in flight, right before the driver's smoke and bench runs on the same box.  It is therefore OPT-IN: FDR_TEST_MPI_HOST=1."""
 import os
 import subprocess
 
@@ -39,7 +40,7 @@ def test_mpi_host_program_builds_and_has_no_cpu_fallback(fdr, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first run is the round-end suite (no GPU was left to try it); ranks share one device")
+@pytest.mark.skipif(os.environ.get("FDR_TEST_MPI_HOST") != "1", reason="opt-in (FDR_TEST_MPI_HOST=1): never run on hardware yet, see the module docstring")
 @pytest.mark.parametrize("ranks,H,W", [(2, 200, 320), (4, 256, 512)])
 def test_mpi_host_program_restores_like_the_single_gpu_plan(gpu, tmp_path, ranks, H, W):
     torch = pytest.importorskip("torch")
