@@ -532,6 +532,9 @@ def run_sharded_child(args, fdr, torch, dist, world, rank, local_rank, dev):
     limit.start()
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
+    dist.barrier()   # the children's own process group works on this box: from here on a failure is the leg's, not the isolation's
+    torch.cuda.synchronize()
+    open("%s.started%d" % (args.sharded_child, rank), "w").close()
     c4, _, H4, W4, pl4, pa4 = WORKLOADS["rgb16384"]
     try:
         res = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, c4, H4, W4, pl4, pa4, 0xF17E0000 + c4,
@@ -551,7 +554,8 @@ def run_sharded_child(args, fdr, torch, dist, world, rank, local_rank, dev):
 def sharded_leg_isolated(args, dist, world, rank):
     """The row-sharded leg as child processes with their own process group (every rank of this job spawns one child on its
     GPU and waits for it): a crash, a hang or a CUDA error in that leg can then not take the batch measurement -- the line
-    rank 0 is about to print -- with it.  Collective over the parent group (one broadcast).  Returns the result on rank 0."""
+    rank 0 is about to print -- with it.  Collective over the parent group (one broadcast).  Returns (result on rank 0 or
+    None, whether this rank's child got as far as a working process group of its own)."""
     import socket
     import tempfile
     info = [None]
@@ -588,8 +592,12 @@ def sharded_leg_isolated(args, dist, world, rank):
             why = "did not finish within %d s" % args.sharded_timeout
     except Exception as e:
         why = "could not start the child: %s" % e
+    marker = "%s.started%d" % (path, rank)
+    started = os.path.exists(marker)
+    if started:
+        os.unlink(marker)
     if rank != 0:
-        return None
+        return None, started
     res = None
     try:
         if os.path.exists(path):
@@ -602,7 +610,7 @@ def sharded_leg_isolated(args, dist, world, rank):
         res = {"unavailable": "row-sharded leg (child processes): %s" % (why or "no result written")}
     res["isolation"] = ("own process group, one child process per rank on the same GPUs (a failure in this leg cannot take the batch "
                         "measurement with it); %.0f s including start-up" % (time.perf_counter() - t0))
-    return res
+    return res, started
 
 
 def side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, our_value):
@@ -685,7 +693,7 @@ def main():
                          "against this library's single-GPU path, or nothing")
     ap.add_argument("--no-sharded", action="store_true", help="N>1, batch workload: skip the row-sharded 16384^2 leg (BASELINE configs[4])")
     ap.add_argument("--sharded-steps", type=int, default=20)
-    ap.add_argument("--sharded-timeout", type=int, default=300, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
+    ap.add_argument("--sharded-timeout", type=int, default=240, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
     ap.add_argument("--sharded-inprocess", action="store_true", help="run the row-sharded leg inside the ranks of this job instead of child processes")
     ap.add_argument("--sharded-child", default="", help=argparse.SUPPRESS)   # internal: see run_sharded_child
     ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
@@ -859,12 +867,6 @@ def main():
         --sharded-inprocess: in this process under a watchdog -- whatever happens in it short of a crash (a rank failing, a
         barrier that never completes), rank 0 still prints the batch line, with the reason instead of the numbers, and every
         rank exits."""
-        if not args.sharded_inprocess:
-            try:
-                return sharded_leg_isolated(args, dist, world, rank)
-            except Exception as e:
-                return {"unavailable": ("%s: %s" % (type(e).__name__, e))[:300]}
-
         def abort():
             try:
                 if rank == 0 and line is not None:
@@ -872,9 +874,30 @@ def main():
                     emit(line)
             finally:
                 os._exit(0)
-        wd = threading.Timer(args.sharded_timeout, abort)
-        wd.daemon = True
-        wd.start()
+
+        def watchdog(seconds):
+            t = threading.Timer(seconds, abort)
+            t.daemon = True
+            t.start()
+            return t
+
+        fell_back = None
+        if not args.sharded_inprocess:
+            wd = watchdog(args.sharded_timeout + 150)   # the children are killed at sharded_timeout; the rest is slack for the decision below
+            try:
+                res, started = sharded_leg_isolated(args, dist, world, rank)
+            except Exception as e:
+                res, started = {"unavailable": ("%s: %s" % (type(e).__name__, e))[:300]}, True
+            # Children that never got a working process group of their own (this box cannot run a second set of ranks on the
+            # same GPUs) say nothing about the leg itself: then, and only then, run it in process.  Decided collectively.
+            ok = rank == 0 and isinstance(res, dict) and "unavailable" not in res
+            vote = torch.tensor([1.0 if ok else 0.0, 0.0 if started else 1.0], dtype=torch.float64, device=dev)
+            dist.all_reduce(vote, op=dist.ReduceOp.MAX)
+            wd.cancel()
+            if vote[0].item() > 0 or vote[1].item() == 0:
+                return res
+            fell_back = (res or {}).get("unavailable", "children did not start")
+        wd = watchdog(args.sharded_timeout)
         try:
             c4, _, H4, W4, pl4, pa4 = WORKLOADS["rgb16384"]
             res = sharded_measure(args, fdr, torch, dist, world, rank, local_rank, dev, c4, H4, W4, pl4, pa4, 0xF17E0000 + c4,
@@ -883,6 +906,8 @@ def main():
         except Exception as e:  # keep the batch line; the other ranks leave through their own watchdogs
             res = {"unavailable": ("%s: %s" % (type(e).__name__, e))[:300]}
         wd.cancel()
+        if fell_back is not None:
+            res["isolation"] = "none: the child processes could not form their own process group (%s), so the leg ran inside the ranks of the job" % fell_back
         return res
 
     if rank != 0:

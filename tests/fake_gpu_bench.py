@@ -11,7 +11,7 @@ reachable from the product or from bench.py itself: the stand-ins are installed 
 
 Environment: FAKE_TMP (directory shared by the ranks), FAKE_HANG_RANK (that rank never returns from phase 1 of the sharded
 leg: exercises the watchdog), FAKE_RAISE_RANK (that rank raises inside the sharded leg), FAKE_CRASH_RANK (that rank's process
-kills itself inside the sharded leg)."""
+kills itself inside the sharded leg), FAKE_CHILD_NO_START (the child processes of the isolated leg exit at once)."""
 import contextlib
 import ctypes
 import os
@@ -336,6 +336,8 @@ def make_fake_fdr():
 
 
 def main():
+    if os.environ.get("FAKE_CHILD_NO_START") == "1" and "--sharded-child" in sys.argv:
+        return 7   # a box on which the children of the isolated sharded leg cannot even start
     install_fake_cuda()
     import bench
     fake_fdr = make_fake_fdr()

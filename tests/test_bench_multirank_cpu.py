@@ -126,3 +126,13 @@ def test_single_rank_line(tmp_path):
     assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"]
     assert d["roofline"]["kernel"] == "pass2_cols_wiener" and d["roofline"]["isolated"]["frac"] > 0
     assert {"serial", "simd", "openmp"} <= set(d.get("cpu_baselines", {"serial": 0, "simd": 0, "openmp": 0}))
+
+
+def test_children_that_cannot_start_fall_back_to_the_in_process_leg(tmp_path):
+    """Only when the children never got a process group of their own (an environment limit, not a failure of the leg)."""
+    r, lines = run_fake_bench(tmp_path, base_port() + 6, ["--sharded-timeout", "30"], {"FAKE_CHILD_NO_START": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1
+    s = json.loads(lines[0])["sharded"]
+    assert "unavailable" not in s, s
+    assert s["isolation"].startswith("none:") and s["parity"]["off_by_more"] == 0 and s["n_gpus"] == 2
