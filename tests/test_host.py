@@ -87,3 +87,37 @@ def test_compat_png_reader_matches_cv2(tmp_path):
     got = np.fromfile(raw, np.uint8).reshape(want.shape)
     assert np.array_equal(got, want)
     assert np.array_equal(cv2.imread(str(out), cv2.IMREAD_COLOR), want)
+
+
+def test_cpp_layer_defines_the_symbols_the_reference_header_declares(tmp_path):
+    """Drop-in at link level: a translation unit that includes the REFERENCE's own fft/fft.hpp
+    (fft.hpp:31-45) and takes the address of every fft_gpu:: function must link against this repository's fft/fft_gpu.cpp
+    compiled in its `<opencv2/opencv.hpp>` branch (here: the oracle's header stand-in for OpenCV) -- i.e. the mangled names
+    and signatures agree, not just the spelling.  Needs /root/reference (build container only)."""
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "fft", "fft.hpp")):
+        pytest.skip("reference sources not present on this box")
+    shim = os.path.join(ROOT, "oracle", "cvshim")
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    probe = tmp_path / "probe.cpp"
+    probe.write_text('#include "fft/fft.hpp"\n'
+                     'void* const fdr_probe[] = {(void*)&fft_gpu::wienerDeblur_RGB_naive, (void*)&fft_gpu::wienerDeblur_RGB_optimized,\n'
+                     '    (void*)&fft_gpu::fft_radix2_kernel, (void*)&fft_gpu::dft_naive_kernel, (void*)&fft_gpu::transform_row_kernel,\n'
+                     '    (void*)&fft_gpu::my_dft2D, (void*)&fft_gpu::wienerDeblur_myfft};\n'
+                     'int main() { return fdr_probe[0] == nullptr; }\n')
+    subprocess.run(["g++", "-std=c++17", "-O0", "-w", "-I", shim, "-I", ref, "-c", str(probe), "-o", str(tmp_path / "probe.o")],
+                   check=True, env=env)
+    # this repository's host layer in the OpenCV branch of fft/fft.hpp (no FDR_FORCE_COMPAT_MAT)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", shim, "-I", PKG, "-I", os.path.join(ROOT, "include"), "-c",
+                    os.path.join(PKG, "fft", "fft_gpu.cpp"), "-o", str(tmp_path / "fft_gpu.o")], check=True, env=env)
+
+    def syms(obj, flag):
+        out = subprocess.run(["nm", flag, str(obj)], capture_output=True, text=True, check=True).stdout
+        return {ln.split()[-1] for ln in out.splitlines() if "fft_gpu" in ln}
+
+    wanted = syms(tmp_path / "probe.o", "--undefined-only")
+    have = syms(tmp_path / "fft_gpu.o", "--defined-only")
+    assert len(wanted) == 7 and wanted <= have, (sorted(wanted - have), sorted(have))
+    subprocess.run(["g++", "-o", str(tmp_path / "probe"), str(tmp_path / "probe.o"), str(tmp_path / "fft_gpu.o"),
+                    "-L", os.path.join(PKG, "lib"), "-lfdr_b200", "-Wl,-rpath," + os.path.join(PKG, "lib")], check=True, env=env)
