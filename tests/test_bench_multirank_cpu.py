@@ -99,7 +99,8 @@ def test_failure_inside_the_sharded_leg_keeps_the_batch_line(tmp_path, bad_rank,
 def test_batch_line_survives_a_crashing_child(tmp_path):
     """A child that dies outright (SIGKILL itself in phase 1) -- the case the in-process form cannot survive, because the
     launcher tears every rank down when one dies."""
-    r, lines = run_fake_bench(tmp_path, base_port() + 5, ["--sharded-timeout", "20"], {"FAKE_CRASH_RANK": "1"})
+    # generous limit: it only runs out if the children are very slow to start (then the in-process fallback would meet the crash)
+    r, lines = run_fake_bench(tmp_path, base_port() + 5, ["--sharded-timeout", "90"], {"FAKE_CRASH_RANK": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(lines) == 1
     d = json.loads(lines[0])
