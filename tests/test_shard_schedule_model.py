@@ -222,3 +222,35 @@ def test_native_driver_schedule_has_no_unordered_conflicts(G, staged):
 def test_model_detects_a_dropped_wait(drop, staged):
     """Negative controls: the checker is only worth something if it sees the races it is meant to exclude."""
     assert build(4, 3, staged, drop=drop).races() != []
+
+
+# ---- the pipelined HOST entry point (csrc/capi.cu, fdr_restore_images_host_u8): H2D of chunk k+1, restoration of chunk k and
+# D2H of chunk k-1 on three streams over double-buffered device staging; the reference does memcpy -> H2D -> compute -> D2H ->
+# sync serially per channel (fft_gpu.cu:347-349, 373-374) ----
+def host_pipeline(chunks, drop=None):
+    s = Schedule(1, 1, False, drop)
+    for k in range(chunks):
+        b = k & 1
+        if k >= 2:
+            s.wait(0, ("cmp", b), "in")           # chunk k-2 no longer reads din[b]
+        s.op(0, "in", "H2D %d" % k, reads={("host_in", k)}, writes={("din", b)})
+        s.record(0, ("in", b), "in")
+        s.wait(0, ("in", b), "cmp")
+        if k >= 2:
+            s.wait(0, ("out", b), "cmp")          # chunk k-2's D2H has drained dout[b]
+        s.op(0, "cmp", "restore %d" % k, reads={("din", b)}, writes={("dout", b), ("workspace",)})
+        s.record(0, ("cmp", b), "cmp")
+        s.wait(0, ("cmp", b), "out")
+        s.op(0, "out", "D2H %d" % k, reads={("dout", b)}, writes={("host_out", k)})
+        s.record(0, ("out", b), "out")
+    return s
+
+
+def test_host_pipeline_schedule_has_no_unordered_conflicts():
+    for chunks in (1, 2, 3, 7):
+        assert host_pipeline(chunks).races() == []
+
+
+@pytest.mark.parametrize("drop", [("wait", "cmp", "in"), ("wait", "out", "cmp"), ("wait", "in", "cmp"), ("wait", "cmp", "out")])
+def test_host_pipeline_model_detects_a_dropped_wait(drop):
+    assert host_pipeline(5, drop=drop).races() != []
