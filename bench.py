@@ -613,6 +613,36 @@ def sharded_leg_isolated(args, dist, world, rank):
     return res, started
 
 
+def single_image_lines(timeout_s=150):
+    """The single-image configurations of BASELINE.json (configs[2] 4096^2, configs[4] 16384^2 on ONE GPU, configs[1] car,
+    configs[0] cat geometry) measured by this same script in child processes, so that the line the driver collects carries them
+    with their own clock records: `python bench.py --workload X [--flush-l2] ...` each, trimmed to the numbers.  Small images
+    flush L2 between steps and time every step on its own; 16384^2 skips the oracle check here (minutes of CPU; the GPU test
+    suite and the multi-GPU `sharded.parity` hold it)."""
+    runs = (("rgb4096", ["--flush-l2", "--steps", "20"]), ("rgb16384", ["--steps", "10", "--no-check"]),
+            ("car", ["--flush-l2", "--steps", "30"]), ("cat", ["--flush-l2", "--steps", "30"]))
+    out = {}
+    for wl, extra in runs:
+        cmd = [sys.executable, CHILD_ENTRY, "--workload", wl, "--warmup", "3", "--no-cpu-baseline", "--no-side", "--no-e2e"] + extra
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not last:
+                out[wl] = {"unavailable": "rc=%s %s" % (r.returncode, (r.stderr or "")[-200:])}
+                continue
+            d = json.loads(last[-1])
+            rf = d.get("roofline") or {}
+            out[wl] = {"image": d["config"]["image"], "psf": d["config"]["psf"], "l2": d["config"]["l2"],
+                       "ms_per_step": d["ms_per_step"], "value": d["value"], "unit": d["unit"], "steps": d["steps"],
+                       "gpu_launches_per_step": d["gpu_launches"] / max(1, d["steps"]), "clocks": d["clocks"], "parity": d["parity"],
+                       "kernels_in_step": (rf.get("in_step") or {}).get("kernels"), "pipeline": rf.get("pipeline"),
+                       "command": "bench.py " + " ".join(cmd[2:]), "wall_s": round(time.perf_counter() - t0, 1)}
+        except Exception as e:
+            out[wl] = {"unavailable": ("%s: %s" % (type(e).__name__, e))[:200]}
+    return out
+
+
 def side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, our_value):
     """Same B200, same run: (1) the reference's own gpu mode (fft/fft_gpu.cu compiled unmodified for sm_100a,
     oracle/_ref/libref_gpu.so) through its 3-plane host boundary as gpu.cpp:96-105 times it, beside this library through the
@@ -696,6 +726,7 @@ def main():
     ap.add_argument("--sharded-timeout", type=int, default=240, help="seconds after which the row-sharded leg is abandoned (the batch line is still printed)")
     ap.add_argument("--sharded-inprocess", action="store_true", help="run the row-sharded leg inside the ranks of this job instead of child processes")
     ap.add_argument("--sharded-child", default="", help=argparse.SUPPRESS)   # internal: see run_sharded_child
+    ap.add_argument("--no-singles", action="store_true", help="N=1, default workload: skip the single-image configurations (child runs of this script)")
     ap.add_argument("--no-side", action="store_true", help="N=1: skip the side comparisons (reference gpu mode, cuFFT) and the extra CPU modes")
     args = ap.parse_args()
     claim_stdout()
@@ -1039,6 +1070,14 @@ def main():
         cpu_baselines["sample"] = "1 image of %dx%dx3 per mode, reference sources compiled unmodified (oracle/_ref)" % (H, W)
 
     _trace('cpu baselines done')
+    singles = None
+    if world == 1 and args.workload == "batch256x2048" and not args.no_side and not args.no_singles:
+        del d_in, d_out
+        plan.close()
+        plan = None
+        torch.cuda.empty_cache()
+        singles = single_image_lines()
+    _trace('single images done')
     line = {
         "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
         "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -1057,6 +1096,8 @@ def main():
         line["cpu_baselines"] = cpu_baselines
     if side:
         line["side"] = side
+    if singles:
+        line["single_images"] = singles
     if run_shard_leg:
         line["sharded"] = sharded_leg(line)
     emit(line)

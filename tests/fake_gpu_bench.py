@@ -357,6 +357,9 @@ def main():
     bench.WORKLOADS = dict(bench.WORKLOADS)
     bench.WORKLOADS["batch256x2048"] = (3, 2, small, small + 16, 5, 30.0)
     bench.WORKLOADS["rgb16384"] = (4, 1, small + 8, small, 5, 30.0)
+    bench.WORKLOADS["rgb4096"] = (2, 1, small, small, 5, 30.0)
+    bench.WORKLOADS["car"] = (1, 1, 33, 64, 5, 45.0)
+    bench.WORKLOADS["cat"] = (0, 1, 78, 96, 5, 30.0)
     return bench.main()
 
 

@@ -123,6 +123,13 @@ def test_single_rank_line(tmp_path):
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["n_gpus"] == 1 and "sharded" not in d
+    singles = d["single_images"]   # BASELINE configs[2], [4] on one GPU, [1], [0]: child runs of the same script
+    assert set(singles) == {"rgb4096", "rgb16384", "car", "cat"}
+    for wl, r in singles.items():
+        assert "unavailable" not in r, (wl, r)
+        assert r["ms_per_step"] > 0 and r["value"] > 0 and r["clocks"]["samples"] > 0 and r["gpu_launches_per_step"] > 0
+        assert (r["parity"] is None) == (wl == "rgb16384")
+        assert r["parity"] is None or r["parity"]["off_by_more"] == 0
     assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"]
     assert d["roofline"]["kernel"] == "pass2_cols_wiener" and d["roofline"]["isolated"]["frac"] > 0
