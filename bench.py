@@ -613,7 +613,7 @@ def sharded_leg_isolated(args, dist, world, rank):
     return res, started
 
 
-def single_image_lines(timeout_s=150):
+def single_image_lines(timeout_s=120):
     """The single-image configurations of BASELINE.json (configs[2] 4096^2, configs[4] 16384^2 on ONE GPU, configs[1] car,
     configs[0] cat geometry) measured by this same script in child processes, so that the line the driver collects carries them
     with their own clock records: `python bench.py --workload X [--flush-l2] ...` each, trimmed to the numbers.  Small images
