@@ -643,6 +643,57 @@ def single_image_lines(timeout_s=120):
     return out
 
 
+def sample_image_comparisons():
+    """BASELINE configs[1] / configs[0] as the reference states them -- `./gpu input/car_blurred.png 40 45`, `... cat_blurred.png
+    50 30` -- on the repo's two sample images: this repository's CLI (the reference's own timing lines, gpu.cpp:96-113) beside
+    the reference's unmodified gpu mode (fft_gpu.cu via oracle/_ref/libref_gpu.so) and its openmp / serial modes on the same
+    geometry, all in this run.  Child processes; side comparisons only."""
+    import re
+    out = {}
+    exe = os.path.join(PKG, "gpu")
+    O = _load("fdr_oracle", os.path.join(ROOT, "oracle", "oracle.py"))
+    for name, wl in (("car_blurred.png", "car"), ("cat_blurred.png", "cat")):
+        cfg_idx, _, H, W, plen, pang = WORKLOADS[wl]
+        png = os.path.join(ROOT, "tests", "golden", "input", name)
+        e = {"image": [H, W, 3], "psf": [plen, pang]}
+        try:
+            r = subprocess.run([exe, png, str(plen), str(pang)], capture_output=True, text=True, timeout=120)
+            m1 = re.search(r"took\(gpu\[optimize\]\): ([0-9.eE+-]+) ms", r.stdout)
+            m2 = re.search(r"took\(gpu\): ([0-9.eE+-]+) ms", r.stdout)
+            if r.returncode == 0 and m1:
+                ms = float(m1.group(1))
+                e["cli"] = {"command": "./gpu tests/golden/input/%s %d %g" % (name, plen, pang), "gpu_optimize_ms": ms,
+                            "gpu_naive_ms": float(m2.group(1)) if m2 else None, "Mpixel/s": H * W / (ms * 1e-3) / 1e6,
+                            "what": "wall clock of fft_gpu::wienerDeblur_RGB_optimized as the CLI prints it (3 f32 host planes in and "
+                                    "out: plan, PSF spectrum, H2D, four passes, D2H inside the timed call), second call"}
+            else:
+                e["cli"] = {"unavailable": "rc=%s %s" % (r.returncode, (r.stderr or r.stdout)[-200:])}
+        except Exception as ex:
+            e["cli"] = {"unavailable": str(ex)[:200]}
+        try:
+            if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_gpu.so")):
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "side_refgpu.py"), str(H), str(W), str(plen), str(pang)],
+                                   capture_output=True, text=True, timeout=180)
+                last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                e["reference_gpu_mode"] = json.loads(last[-1]) if (r.returncode == 0 and last) else \
+                    {"unavailable": "rc=%d %s" % (r.returncode, (r.stderr or r.stdout)[-200:])}
+        except Exception as ex:
+            e["reference_gpu_mode"] = {"unavailable": str(ex)[:200]}
+        try:
+            if O.have_ref():
+                psf = O.port().motion_psf(plen, pang)
+                threads = os.cpu_count() or 1
+                cpu_restore_images(O, "openmp", cfg_idx, 0, 1, H, W, psf, threads)   # first call starts the thread pool
+                t_omp = cpu_restore_images(O, "openmp", cfg_idx, 0, 1, H, W, psf, threads)
+                t_ser = cpu_restore_images(O, "serial", cfg_idx, 0, 1, H, W, psf, 1)
+                e["reference_cpu"] = {"openmp_ms": t_omp * 1e3, "openmp_threads": threads, "serial_ms": t_ser * 1e3,
+                                      "what": "reference fft_openmp.cpp / fft_serial.cpp compiled unmodified, 3 planes of this geometry"}
+        except Exception as ex:
+            e["reference_cpu"] = {"unavailable": str(ex)[:200]}
+        out[name] = e
+    return out
+
+
 def side_comparisons(fdr, torch, plan, d_in, d_out, stream, H, W, plen, pang, our_value):
     """Same B200, same run: (1) the reference's own gpu mode (fft/fft_gpu.cu compiled unmodified for sm_100a,
     oracle/_ref/libref_gpu.so) through its 3-plane host boundary as gpu.cpp:96-105 times it, beside this library through the
@@ -1070,13 +1121,17 @@ def main():
         cpu_baselines["sample"] = "1 image of %dx%dx3 per mode, reference sources compiled unmodified (oracle/_ref)" % (H, W)
 
     _trace('cpu baselines done')
-    singles = None
+    singles = samples = None
     if world == 1 and args.workload == "batch256x2048" and not args.no_side and not args.no_singles:
         del d_in, d_out
         plan.close()
         plan = None
         torch.cuda.empty_cache()
         singles = single_image_lines()
+        try:
+            samples = sample_image_comparisons()
+        except Exception as e:
+            samples = {"unavailable": ("%s: %s" % (type(e).__name__, e))[:200]}
     _trace('single images done')
     line = {
         "metric": "Mpixel/s deblurred (FFT->Wiener->IFFT->normalise->8-bit pack)",
@@ -1098,6 +1153,8 @@ def main():
         line["side"] = side
     if singles:
         line["single_images"] = singles
+    if samples:
+        line["sample_images"] = samples
     if run_shard_leg:
         line["sharded"] = sharded_leg(line)
     emit(line)

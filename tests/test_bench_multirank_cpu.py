@@ -125,6 +125,10 @@ def test_single_rank_line(tmp_path):
     assert d["n_gpus"] == 1 and "sharded" not in d
     singles = d["single_images"]   # BASELINE configs[2], [4] on one GPU, [1], [0]: child runs of the same script
     assert set(singles) == {"rgb4096", "rgb16384", "car", "cat"}
+    samples = d["sample_images"]   # the CLI on the repo's two sample images beside the reference's gpu / openmp / serial modes
+    assert set(samples) == {"car_blurred.png", "cat_blurred.png"}
+    for e in samples.values():     # no device here: the GPU legs must say so instead of inventing numbers
+        assert "unavailable" in e["cli"] and e["reference_cpu"]["serial_ms"] > 0
     for wl, r in singles.items():
         assert "unavailable" not in r, (wl, r)
         assert r["ms_per_step"] > 0 and r["value"] > 0 and r["clocks"]["samples"] > 0 and r["gpu_launches_per_step"] > 0
