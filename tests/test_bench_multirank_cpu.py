@@ -148,3 +148,14 @@ def test_children_that_cannot_start_fall_back_to_the_in_process_leg(tmp_path):
     s = json.loads(lines[0])["sharded"]
     assert "unavailable" not in s, s
     assert s["isolation"].startswith("none:") and s["parity"]["off_by_more"] == 0 and s["n_gpus"] == 2
+
+
+def test_explicit_sharded_workload_is_the_line_itself(tmp_path):
+    """`--workload rgb16384 --gpus N`: the row-sharded measurement as the contract line (strong scaling)."""
+    r, lines = run_fake_bench(tmp_path, base_port() + 7, ["--workload", "rgb16384"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["scaling"] == "strong" and d["n_gpus"] == 2 and d["config"]["workload"] == "rgb16384"
+    assert d["parity"]["off_by_more"] == 0 and d["clocks"]["samples"] > 0 and d["roofline"]["kernel"] == "phase2_cols_wiener"
+    assert d["sharded"]["e2e"]["matches_device"] is True
